@@ -1,0 +1,688 @@
+// lins_gpu.cu — C-ABI implementation (include/lins_gpu.h) + the fused IESKF kernel entry points, sm_100a.
+// Host side is plain C++ / CUDA runtime: no torch, no Eigen, no PCL in any signature.  There is NO CPU
+// fallback: every entry point fails with LINS_E_NODEVICE / LINS_E_CUDA when the device path is unavailable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lins_kernels.cuh"
+
+using namespace lins_dev;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// dynamic shared memory layout: [qpt float4 x Q][sel float4 x Q][key u64 x Q][ind int x 3Q][Smem]
+// ---------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t smem_bytes_for(int qtile) {
+  size_t b = (size_t)qtile * (16 + 16 + 8 + 12);
+  b = (b + 15) & ~(size_t)15;
+  return b + sizeof(Smem) + 16;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_constant__ BatchView bv,
+                                                              const __grid_constant__ KParams kp) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int Q = bv.qtile;
+  float4* qpt = reinterpret_cast<float4*>(smem_raw);
+  float4* selbuf = qpt + Q;
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(selbuf + Q);
+  int* indbuf = reinterpret_cast<int*>(key + Q);
+  size_t off = (size_t)Q * (16 + 16 + 8 + 12);
+  off = (off + 15) & ~(size_t)15;
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + off);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double sig2 = kp.lidar_std * kp.lidar_std;
+
+  if (tid == 0) {
+    mbar_init(&sm.mbar, 1);
+    sm.phase = 0;
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  for (;;) {
+    if (tid == 0) sm.scan = atomicAdd(bv.work_counter, 1);
+    __syncthreads();
+    const int scan = sm.scan;
+    if (scan >= bv.n_scans) break;
+
+    // ---- prior -> shared ---------------------------------------------------------------------------------
+    if (tid < 20) { double v = tid < 19 ? bv.state_in[(size_t)scan * 20 + tid] : 0.0; sm.prior[tid] = v; sm.lin[tid] = v; }
+    for (int e = tid; e < 324; e += kThreads) {
+      const int r = e / 18, c = e % 18;
+      sm.P[e] = bv.cov_in[(size_t)scan * 324 + c * 18 + r];
+    }
+    if (tid == 0) { sm.flags[0] = sm.flags[1] = sm.flags[2] = sm.flags[3] = 0; sm.residualNorm = 1e6; }
+    {
+      const int ts0 = bv.ts_off[scan], Ts = bv.ts_off[scan + 1] - ts0;
+      const int tc0 = bv.tc_off[scan], Tc = bv.tc_off[scan + 1] - tc0;
+      build_ring_table(bv.ts + ts0, Ts, sm.rsS, &sm.sortedS);
+      build_ring_table(bv.tc + tc0, Tc, sm.rsC, &sm.sortedC);
+    }
+    lins_report* rep = bv.reports ? bv.reports + scan : nullptr;
+    int iters = 0;
+
+    if (MODE == MODE_ASSOC || MODE == MODE_ICP_REDUCE) {
+      if (tid == 0) compute_iter_consts(sm);
+      __syncthreads();
+      association_pass<MODE>(sm, bv, kp, scan, kp.iter0, qpt, selbuf, key, indbuf);
+      if (bv.accum) {
+        if (tid < kNAcc) bv.accum[(size_t)scan * 32 + tid] = sm.acc[tid];
+        if (tid == 32) { bv.accum[(size_t)scan * 32 + 28] = (double)sm.cnt[0]; bv.accum[(size_t)scan * 32 + 29] = (double)sm.cnt[1]; }
+      }
+      __syncthreads();
+      continue;
+    }
+
+    // ---- the iterated update (StateEstimator.hpp:475-581) ---------------------------------------------------
+    for (int iter = 0; iter < kp.num_iter; ++iter) {
+      if (tid == 0) compute_iter_consts(sm);
+      __syncthreads();
+      association_pass<MODE>(sm, bv, kp, scan, iter, qpt, selbuf, key, indbuf);
+      build_A6(sm);
+      if (tid == 128) box_minus(sm);
+      __syncthreads();
+      if (tid < 6) {  // y = b + A d on the 6 structural rows
+        double s = sm.y6[tid];
+        for (int c = 0; c < 6; ++c) s += sm.A6[tid * 6 + c] * sm.dvec[col6(c)];
+        sm.y6[tid] = s;
+      }
+      form_S(sm, sig2);
+      __syncthreads();
+      if (tid < 18) {  // rhs = P y
+        double s = 0;
+        for (int c = 0; c < 6; ++c) s += sm.P[tid * 18 + col6(c)] * sm.y6[c];
+        sm.B[tid] = s;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        const bool ok = warp_lu_solve(sm.S, sm.B, 1);
+        if (lane == 0) {
+          bool hasNaN = false;
+          for (int a = 0; a < 18; ++a) {
+            double u = ok ? (-sm.B[a] + sm.dvec[a]) : __longlong_as_double(0x7ff8000000000000ll);
+            if (u != u) { u = 0.0; hasNaN = true; }  // :553-558
+            sm.upd[a] = u;
+          }
+          double un = 0;
+          for (int a = 0; a < 18; ++a) un += sm.upd[a] * sm.upd[a];
+          un = sqrt(un);
+          const double rnorm = sqrt(sm.acc[27]);
+          if (rep) {
+            rep->m_surf[iter] = sm.cnt[0]; rep->m_corner[iter] = sm.cnt[1];
+            rep->residual_norm[iter] = rnorm; rep->update_norm[iter] = un;
+          }
+          if (hasNaN) {  // :559-563
+            sm.flags[2] = 1; sm.flags[1] = 1; sm.flags[3] = 1;
+          } else if (rnorm > sm.residualNorm * 10) {  // :566-570
+            sm.flags[1] = 1; sm.flags[3] = 1;
+          } else {
+            box_plus(sm);  // :573
+            if (un <= 1e-2 && !kp.force_all_iters) { sm.flags[0] = 1; sm.flags[3] = 1; }  // :576-578
+            sm.residualNorm = rnorm;
+          }
+        }
+      }
+      __syncthreads();
+      iters = iter + 1;
+      if (sm.flags[3]) break;
+    }
+
+    // ---- exit: covariance + outputs (StateEstimator.hpp:585-599) -------------------------------------------
+    const bool diverged = sm.flags[1] != 0;
+    if (!diverged && iters > 0) {
+      // G = (P A + sig2 I)^-1 P ; K H = G A ; K R K^T = sig2 G A G^T
+      form_S(sm, sig2);
+      for (int e = tid; e < 324; e += kThreads) sm.B[e] = sm.P[e];
+      __syncthreads();
+      if (warp == 0) {
+        const bool ok = warp_lu_solve(sm.S, sm.B, 18);
+        if (!ok) for (int e = lane; e < 324; e += 32) sm.B[e] = __longlong_as_double(0x7ff8000000000000ll);
+      }
+      __syncthreads();
+      for (int e = tid; e < 324; e += kThreads) {  // W2 = G A18 ; W1 = I - G A18
+        const int a = e / 18, c = e % 18;
+        int cc = -1;
+        if (c < 3) cc = c; else if (c >= 6 && c < 9) cc = c - 3;
+        double s = 0;
+        if (cc >= 0) for (int k = 0; k < 6; ++k) s += sm.B[a * 18 + col6(k)] * sm.A6[k * 6 + cc];
+        sm.W2[e] = s;
+        sm.W1[e] = (a == c ? 1.0 : 0.0) - s;
+      }
+      __syncthreads();
+      mat18_mul(sm.S, sm.W1, sm.P, false);  // S = IKH P
+      __syncthreads();
+      for (int e = tid; e < 324; e += kThreads) {  // P <- IKH P IKH^T + sig2 (G A) G^T
+        const int i = e / 18, j = e % 18;
+        double s = 0, t = 0;
+        for (int k = 0; k < 18; ++k) { s += sm.S[i * 18 + k] * sm.W1[j * 18 + k]; t += sm.W2[i * 18 + k] * sm.B[j * 18 + k]; }
+        sm.P[e] = s + t * sig2;
+      }
+      __syncthreads();
+    }
+    // state_out / cov_out
+    if (tid < 20) bv.state_out[(size_t)scan * 20 + tid] = diverged ? sm.prior[tid] : sm.lin[tid];
+    for (int e = tid; e < 324; e += kThreads) {
+      const int r = e / 18, c = e % 18;
+      double v;
+      if (diverged) v = bv.cov_in[(size_t)scan * 324 + c * 18 + r];
+      else if (iters > 0) v = 0.5 * (sm.P[r * 18 + c] + sm.P[c * 18 + r]);  // enforceSymmetry (:597)
+      else v = sm.P[r * 18 + c];
+      bv.cov_out[(size_t)scan * 324 + c * 18 + r] = v;
+    }
+    if (tid == 0) {
+      lins_scan_result& o = bv.results[scan];
+      o.scan_id = scan;
+      o.iters = (uint16_t)iters;
+      o.flags = (uint16_t)((sm.flags[0] ? 1 : 0) | (sm.flags[1] ? 2 : 0) | (sm.flags[2] ? 4 : 0));
+      const double* st = diverged ? sm.prior : sm.lin;
+      o.pose[0] = st[0]; o.pose[1] = st[1]; o.pose[2] = st[2];
+      o.pose[3] = st[6]; o.pose[4] = st[7]; o.pose[5] = st[8]; o.pose[6] = st[9];
+      if (rep) { rep->iters = iters; rep->converged = sm.flags[0]; rep->diverged = sm.flags[1]; rep->has_nan = sm.flags[2]; }
+    }
+    __syncthreads();
+  }
+}
+
+// Pack pcl::PointXYZI (32 B AoS) -> float4 (x, y, z, intensity) on device, for clouds uploaded raw.
+__global__ void lins_pack_points_kernel(const lins_point* __restrict__ in, float4* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * (size_t)i);
+    const float b = __ldg(reinterpret_cast<const float*>(in) + 8 * (size_t)i + 4);
+    out[i] = make_float4(a.x, a.y, a.z, b);
+  }
+}
+
+// F1: transformToEnd (StateEstimator.hpp:1083-1101) of a packed cloud, in place on device.
+__global__ void lins_transform_to_end_kernel(float4* __restrict__ pts, int n, const double* __restrict__ lin,
+                                             double scan_period) {
+  __shared__ double sphi[3], srn[3], sq[4];
+  if (threadIdx.x == 0) {
+    q4 q; q.x = lin[6]; q.y = lin[7]; q.z = lin[8]; q.w = lin[9];
+    d3 phi = Quat2axis(q);
+    sphi[0] = phi.x; sphi[1] = phi.y; sphi[2] = phi.z;
+    srn[0] = lin[0]; srn[1] = lin[1]; srn[2] = lin[2];
+    sq[0] = q.x; sq[1] = q.y; sq[2] = q.z; sq[3] = q.w;
+  }
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  float fi = p.w - (float)((int)p.w);
+  double s = (1.f / scan_period) * fi;
+  q4 r = axis2Quat(mk3(s * sphi[0], s * sphi[1], s * sphi[2]));
+  d3 P1 = add3(qrot(r, mk3(p.x, p.y, p.z)), mk3(s * srn[0], s * srn[1], s * srn[2]));
+  q4 q; q.x = sq[0]; q.y = sq[1]; q.z = sq[2]; q.w = sq[3];
+  d3 P2 = qrot(qinverse(q), sub3(P1, mk3(srn[0], srn[1], srn[2])));
+  p.x = (float)P2.x; p.y = (float)P2.y; p.z = (float)P2.z;
+  pts[i] = p;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side helpers
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = std::max<size_t>(n, 16);
+    cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    size_t want = std::max<size_t>(n, 16);
+    cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Resident {  // one resident batch (device) + its pinned staging (host)
+  int n = 0;
+  size_t nqs = 0, nqc = 0, nts = 0, ntc = 0;
+  int max_q = 0;
+  DevBuf<float4> qs, qc, ts, tc;
+  DevBuf<int> qs_off, qc_off, ts_off, tc_off, ind_s, ind_c, counter;
+  DevBuf<double> state_in, cov_in, state_out, cov_out, accum;
+  DevBuf<lins_scan_result> results;
+  DevBuf<lins_report> reports;
+  DevBuf<float> sel_s, sel_c, coeff_s, coeff_c;
+  DevBuf<unsigned char> mask_s, mask_c;
+  PinBuf<float4> h_pts;       // staging for all four clouds, back to back
+  PinBuf<int> h_off;          // 4 x (n+1)
+  PinBuf<double> h_state, h_cov, h_state_out, h_cov_out, h_accum;
+  PinBuf<lins_scan_result> h_results;
+  PinBuf<lins_report> h_reports;
+  void release() {
+    qs.release(); qc.release(); ts.release(); tc.release(); qs_off.release(); qc_off.release(); ts_off.release();
+    tc_off.release(); ind_s.release(); ind_c.release(); counter.release(); state_in.release(); cov_in.release();
+    state_out.release(); cov_out.release(); accum.release(); results.release(); reports.release(); sel_s.release();
+    sel_c.release(); coeff_s.release(); coeff_c.release(); mask_s.release(); mask_c.release(); h_pts.release();
+    h_off.release(); h_state.release(); h_cov.release(); h_state_out.release(); h_cov_out.release();
+    h_accum.release(); h_results.release(); h_reports.release();
+  }
+};
+
+}  // namespace
+
+struct lins_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  lins_params prm;
+  std::string err;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  int64_t launches = 0;
+  Resident batch;   // lins_gpu_batch_* working set
+  Resident single;  // lins_gpu_ieskf / associate / estimate_transform (n = 1)
+  // the single-scan map: "last" clouds (walks + tripods) and the clouds the 1-NN index was built on
+  DevBuf<float4> map_s, map_c, tree_s, tree_c;
+  DevBuf<int> map_off;  // 4 x 2 ints: [0,ns][0,nc][0,tns][0,tnc]
+  int map_ns = -1, map_nc = -1, tree_ns = -1, tree_nc = -1;
+  bool tree_is_map = true;
+  DevBuf<float4> tmp_pts;
+  DevBuf<double> tmp_lin;
+  PinBuf<float4> h_tmp;
+};
+
+namespace {
+
+int fail(lins_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    c->err = what;
+    if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+  }
+  return code;
+}
+#define CK(call)                                                     \
+  do {                                                               \
+    cudaError_t _e = (call);                                         \
+    if (_e != cudaSuccess) return fail(ctx, LINS_E_CUDA, #call, _e); \
+  } while (0)
+
+inline void pack_into(float4* dst, const lins_point* src, int n) {
+  for (int i = 0; i < n; ++i) dst[i] = make_float4(src[i].x, src[i].y, src[i].z, src[i].intensity);
+}
+
+KParams make_kparams(const lins_params& p, int mode, int iter0) {
+  KParams k;
+  k.num_iter = p.num_iter; k.icp_freq = p.icp_freq < 1 ? 1 : p.icp_freq; k.force_all_iters = p.force_all_iters;
+  k.mode = mode; k.iter0 = iter0;
+  k.nearest_sq = p.nearest_feature_search_sq_dist; k.lidar_std = p.lidar_std; k.lidar_scale = p.lidar_scale;
+  k.scan_period = p.scan_period;
+  return k;
+}
+
+int validate_params(const lins_params* p) {
+  if (!p) return LINS_E_INVALID;
+  if (p->num_iter < 0 || p->num_iter > LINS_MAX_ITER) return LINS_E_INVALID;
+  if (p->icp_freq < 1) return LINS_E_INVALID;
+  if (!(p->scan_period > 0)) return LINS_E_INVALID;
+  return LINS_OK;
+}
+
+template <int MODE>
+int launch_mode(lins_ctx* ctx, const BatchView& bv, const KParams& kp) {
+  size_t smem = smem_bytes_for(bv.qtile);
+  if ((int)smem > ctx->max_smem_optin) return fail(ctx, LINS_E_TOOBIG, "query tile does not fit shared memory");
+  CK(cudaFuncSetAttribute(lins_ieskf_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lins_ieskf_kernel<MODE>, kThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = std::min(bv.n_scans, ctx->sm_count * per_sm);
+  if (grid < 1) grid = 1;
+  CK(cudaMemsetAsync(bv.work_counter, 0, sizeof(int), ctx->stream));
+  lins_ieskf_kernel<MODE><<<grid, kThreads, smem, ctx->stream>>>(bv, kp);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  return LINS_OK;
+}
+
+int launch(lins_ctx* ctx, const BatchView& bv, const KParams& kp) {
+  switch (kp.mode) {
+    case MODE_IESKF: return launch_mode<MODE_IESKF>(ctx, bv, kp);
+    case MODE_ASSOC: return launch_mode<MODE_ASSOC>(ctx, bv, kp);
+    case MODE_ICP_REDUCE: return launch_mode<MODE_ICP_REDUCE>(ctx, bv, kp);
+  }
+  return fail(ctx, LINS_E_INVALID, "bad kernel mode");
+}
+
+int choose_qtile(int max_q) {
+  int q = ((max_q + 31) / 32) * 32;
+  if (q < 32) q = 32;
+  if (q > 1024) q = 1024;
+  return q;
+}
+
+// allocate the per-batch outputs / scratch for n scans with the given query totals
+int reserve_outputs(lins_ctx* ctx, Resident& r, bool want_reports, bool want_trace) {
+  CK(r.state_out.reserve((size_t)r.n * 20));
+  CK(r.cov_out.reserve((size_t)r.n * 324));
+  CK(r.results.reserve(r.n));
+  CK(r.accum.reserve((size_t)r.n * 32));
+  CK(r.ind_s.reserve(3 * r.nqs + 4));
+  CK(r.ind_c.reserve(2 * r.nqc + 4));
+  CK(r.counter.reserve(4));
+  if (want_reports) CK(r.reports.reserve(r.n));
+  if (want_trace) {
+    CK(r.sel_s.reserve(3 * r.nqs + 4)); CK(r.sel_c.reserve(3 * r.nqc + 4));
+    CK(r.coeff_s.reserve(4 * r.nqs + 4)); CK(r.coeff_c.reserve(4 * r.nqc + 4));
+    CK(r.mask_s.reserve(r.nqs + 4)); CK(r.mask_c.reserve(r.nqc + 4));
+  }
+  return LINS_OK;
+}
+
+BatchView view_of(const Resident& r, bool reports, bool trace) {
+  BatchView bv;
+  std::memset(&bv, 0, sizeof(bv));
+  bv.n_scans = r.n;
+  bv.qs = r.qs.p; bv.qs_off = r.qs_off.p; bv.qc = r.qc.p; bv.qc_off = r.qc_off.p;
+  bv.ts = r.ts.p; bv.ts_off = r.ts_off.p; bv.tc = r.tc.p; bv.tc_off = r.tc_off.p;
+  bv.state_in = r.state_in.p; bv.cov_in = r.cov_in.p; bv.state_out = r.state_out.p; bv.cov_out = r.cov_out.p;
+  bv.results = r.results.p; bv.reports = reports ? r.reports.p : nullptr;
+  bv.ind_s = r.ind_s.p; bv.ind_c = r.ind_c.p;
+  if (trace) {
+    bv.sel_s = r.sel_s.p; bv.sel_c = r.sel_c.p; bv.coeff_s = r.coeff_s.p; bv.coeff_c = r.coeff_c.p;
+    bv.mask_s = r.mask_s.p; bv.mask_c = r.mask_c.p;
+  }
+  bv.accum = r.accum.p;
+  bv.work_counter = r.counter.p;
+  bv.qtile = choose_qtile(r.max_q);
+  return bv;
+}
+
+// Upload the queries + prior of ONE scan into ctx->single and point its targets at the resident map.
+int stage_single(lins_ctx* ctx, const lins_point* surf_flat, int ns, const lins_point* corner_sharp, int nc,
+                 const double* state_in, const double* cov_in, bool trace) {
+  if (ctx->map_ns < 0) return fail(ctx, LINS_E_NOMAP, "lins_gpu_set_map has not been called");
+  if (ns < 0 || nc < 0 || (ns > 0 && !surf_flat) || (nc > 0 && !corner_sharp)) return fail(ctx, LINS_E_INVALID, "bad query cloud");
+  Resident& r = ctx->single;
+  r.n = 1; r.nqs = ns; r.nqc = nc; r.max_q = ns + nc;
+  CK(r.qs.reserve(ns + 1)); CK(r.qc.reserve(nc + 1));
+  CK(r.qs_off.reserve(2)); CK(r.qc_off.reserve(2));
+  CK(r.state_in.reserve(20)); CK(r.cov_in.reserve(324));
+  CK(r.h_pts.reserve((size_t)ns + nc + 1)); CK(r.h_off.reserve(4)); CK(r.h_state.reserve(20)); CK(r.h_cov.reserve(324));
+  pack_into(r.h_pts.p, surf_flat, ns);
+  pack_into(r.h_pts.p + ns, corner_sharp, nc);
+  r.h_off.p[0] = 0; r.h_off.p[1] = ns; r.h_off.p[2] = 0; r.h_off.p[3] = nc;
+  for (int i = 0; i < 19; ++i) r.h_state.p[i] = state_in[i];
+  r.h_state.p[19] = 0.0;
+  if (cov_in) std::memcpy(r.h_cov.p, cov_in, sizeof(double) * 324); else std::memset(r.h_cov.p, 0, sizeof(double) * 324);
+  if (ns) CK(cudaMemcpyAsync(r.qs.p, r.h_pts.p, sizeof(float4) * ns, cudaMemcpyHostToDevice, ctx->stream));
+  if (nc) CK(cudaMemcpyAsync(r.qc.p, r.h_pts.p + ns, sizeof(float4) * nc, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(r.qs_off.p, r.h_off.p, sizeof(int) * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(r.qc_off.p, r.h_off.p + 2, sizeof(int) * 2, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(r.state_in.p, r.h_state.p, sizeof(double) * 20, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(r.cov_in.p, r.h_cov.p, sizeof(double) * 324, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = reserve_outputs(ctx, r, true, trace);
+  return rc;
+}
+
+BatchView single_view(lins_ctx* ctx, bool trace) {
+  BatchView bv = view_of(ctx->single, true, trace);
+  bv.ts = ctx->map_s.p; bv.ts_off = ctx->map_off.p + 0;
+  bv.tc = ctx->map_c.p; bv.tc_off = ctx->map_off.p + 2;
+  if (!ctx->tree_is_map) {
+    bv.nn_s = ctx->tree_s.p; bv.nn_s_off = ctx->map_off.p + 4;
+    bv.nn_c = ctx->tree_c.p; bv.nn_c_off = ctx->map_off.p + 6;
+  }
+  return bv;
+}
+
+int upload_map_offsets(lins_ctx* ctx) {
+  CK(ctx->map_off.reserve(8));
+  int h[8] = {0, ctx->map_ns, 0, ctx->map_nc, 0, ctx->tree_ns, 0, ctx->tree_nc};
+  CK(cudaMemcpyAsync(ctx->map_off.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // h is on the stack
+  return LINS_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+// C-ABI
+// =========================================================================================================
+extern "C" {
+
+int lins_gpu_abi_version(void) { return 1; }
+
+int lins_gpu_create(const lins_params* params, int device, void* stream, lins_ctx** out) {
+  if (!out) return LINS_E_INVALID;
+  *out = nullptr;
+  if (validate_params(params) != LINS_OK) return LINS_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LINS_E_NODEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return LINS_E_NODEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LINS_E_NODEVICE;
+  if (prop.major != 10) return LINS_E_NODEVICE;  // the fatbin holds sm_100a code only
+  lins_ctx* ctx = new (std::nothrow) lins_ctx();
+  if (!ctx) return LINS_E_INVALID;
+  ctx->device = device;
+  ctx->prm = *params;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LINS_E_CUDA; }
+    ctx->own_stream = true;
+  }
+  *out = ctx;
+  return LINS_OK;
+}
+
+void lins_gpu_destroy(lins_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->batch.release(); ctx->single.release();
+  ctx->map_s.release(); ctx->map_c.release(); ctx->tree_s.release(); ctx->tree_c.release(); ctx->map_off.release();
+  ctx->tmp_pts.release(); ctx->tmp_lin.release(); ctx->h_tmp.release();
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* lins_gpu_last_error(const lins_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int lins_gpu_set_params(lins_ctx* ctx, const lins_params* params) {
+  if (!ctx) return LINS_E_INVALID;
+  if (validate_params(params) != LINS_OK) return fail(ctx, LINS_E_INVALID, "bad params");
+  ctx->prm = *params;
+  return LINS_OK;
+}
+
+int64_t lins_gpu_launch_count(const lins_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lins_gpu_set_map(lins_ctx* ctx, const lins_point* surf, int ns, const lins_point* corner, int nc) {
+  if (!ctx) return LINS_E_INVALID;
+  if (ns < 0 || nc < 0 || (ns > 0 && !surf) || (nc > 0 && !corner)) return fail(ctx, LINS_E_INVALID, "bad map cloud");
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->map_s.reserve(ns + 1)); CK(ctx->map_c.reserve(nc + 1));
+  CK(ctx->h_tmp.reserve((size_t)ns + nc + 1));
+  pack_into(ctx->h_tmp.p, surf, ns);
+  pack_into(ctx->h_tmp.p + ns, corner, nc);
+  if (ns) CK(cudaMemcpyAsync(ctx->map_s.p, ctx->h_tmp.p, sizeof(float4) * ns, cudaMemcpyHostToDevice, ctx->stream));
+  if (nc) CK(cudaMemcpyAsync(ctx->map_c.p, ctx->h_tmp.p + ns, sizeof(float4) * nc, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->map_ns = ns; ctx->map_nc = nc; ctx->tree_ns = ns; ctx->tree_nc = nc; ctx->tree_is_map = true;
+  return upload_map_offsets(ctx);
+}
+
+int lins_gpu_ieskf(lins_ctx* ctx, const lins_point* surf_flat, int ns, const lins_point* corner_sharp, int nc,
+                   const double* state_in, const double* cov_in, double* state_out, double* cov_out, lins_report* rep) {
+  if (!ctx) return LINS_E_INVALID;
+  if (!state_in || !cov_in) return fail(ctx, LINS_E_INVALID, "null prior");
+  CK(cudaSetDevice(ctx->device));
+  int rc = stage_single(ctx, surf_flat, ns, corner_sharp, nc, state_in, cov_in, false);
+  if (rc != LINS_OK) return rc;
+  Resident& r = ctx->single;
+  BatchView bv = single_view(ctx, false);
+  CK(cudaMemsetAsync(r.reports.p, 0, sizeof(lins_report), ctx->stream));
+  rc = launch(ctx, bv, make_kparams(ctx->prm, MODE_IESKF, 0));
+  if (rc != LINS_OK) return rc;
+  CK(r.h_state_out.reserve(20)); CK(r.h_cov_out.reserve(324)); CK(r.h_reports.reserve(1));
+  CK(cudaMemcpyAsync(r.h_state_out.p, r.state_out.p, sizeof(double) * 20, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(r.h_cov_out.p, r.cov_out.p, sizeof(double) * 324, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(r.h_reports.p, r.reports.p, sizeof(lins_report), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (state_out) std::memcpy(state_out, r.h_state_out.p, sizeof(double) * 19);
+  if (cov_out) std::memcpy(cov_out, r.h_cov_out.p, sizeof(double) * 324);
+  if (rep) *rep = r.h_reports.p[0];
+  return LINS_OK;
+}
+
+int lins_gpu_associate(lins_ctx* ctx, const lins_point* surf_flat, int ns, const lins_point* corner_sharp, int nc,
+                       const double* lin_state, int iter, int32_t* surf_ind, int32_t* corner_ind, float* surf_coeff,
+                       float* corner_coeff, uint8_t* surf_mask, uint8_t* corner_mask, float* surf_sel, float* corner_sel) {
+  if (!ctx) return LINS_E_INVALID;
+  if (!lin_state || iter < 0) return fail(ctx, LINS_E_INVALID, "bad lin_state / iter");
+  CK(cudaSetDevice(ctx->device));
+  // pointSearch*Ind persist on device between calls (buffers are only re-allocated when they must grow)
+  int rc = stage_single(ctx, surf_flat, ns, corner_sharp, nc, lin_state, nullptr, true);
+  if (rc != LINS_OK) return rc;
+  Resident& r = ctx->single;
+  BatchView bv = single_view(ctx, true);
+  rc = launch(ctx, bv, make_kparams(ctx->prm, MODE_ASSOC, iter));
+  if (rc != LINS_OK) return rc;
+  auto d2h = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+    if (!dst || bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  };
+  CK(d2h(surf_ind, r.ind_s.p, sizeof(int) * 3 * ns));
+  CK(d2h(corner_ind, r.ind_c.p, sizeof(int) * 2 * nc));
+  CK(d2h(surf_coeff, r.coeff_s.p, sizeof(float) * 4 * ns));
+  CK(d2h(corner_coeff, r.coeff_c.p, sizeof(float) * 4 * nc));
+  CK(d2h(surf_mask, r.mask_s.p, ns));
+  CK(d2h(corner_mask, r.mask_c.p, nc));
+  CK(d2h(surf_sel, r.sel_s.p, sizeof(float) * 3 * ns));
+  CK(d2h(corner_sel, r.sel_c.p, sizeof(float) * 3 * nc));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LINS_OK;
+}
+
+// ---- batched mode ----------------------------------------------------------------------------------------
+int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
+  if (!ctx) return LINS_E_INVALID;
+  if (!b || b->n_scans < 0) return fail(ctx, LINS_E_INVALID, "bad batch");
+  CK(cudaSetDevice(ctx->device));
+  Resident& r = ctx->batch;
+  const int n = b->n_scans;
+  r.n = n;
+  if (n == 0) return LINS_OK;
+  const int32_t* offs[4] = {b->surf_flat_off, b->corner_sharp_off, b->surf_less_flat_off, b->corner_less_sharp_off};
+  const lins_point* pts[4] = {b->surf_flat, b->corner_sharp, b->surf_less_flat, b->corner_less_sharp};
+  for (int k = 0; k < 4; ++k) {
+    if (!offs[k]) return fail(ctx, LINS_E_INVALID, "null offsets");
+    if (offs[k][0] != 0) return fail(ctx, LINS_E_INVALID, "offsets must start at 0");
+    for (int i = 0; i < n; ++i) if (offs[k][i + 1] < offs[k][i]) return fail(ctx, LINS_E_INVALID, "offsets must be non-decreasing");
+    if (offs[k][n] > 0 && !pts[k]) return fail(ctx, LINS_E_INVALID, "null cloud");
+  }
+  if (!b->state_in || !b->cov_in) return fail(ctx, LINS_E_INVALID, "null prior");
+  r.nqs = offs[0][n]; r.nqc = offs[1][n]; r.nts = offs[2][n]; r.ntc = offs[3][n];
+  r.max_q = 0;
+  for (int i = 0; i < n; ++i) r.max_q = std::max(r.max_q, (offs[0][i + 1] - offs[0][i]) + (offs[1][i + 1] - offs[1][i]));
+  const size_t total = r.nqs + r.nqc + r.nts + r.ntc;
+  CK(r.h_pts.reserve(total + 1)); CK(r.h_off.reserve(4 * (size_t)(n + 1)));
+  CK(r.h_state.reserve((size_t)n * 20)); CK(r.h_cov.reserve((size_t)n * 324));
+  CK(r.qs.reserve(r.nqs + 1)); CK(r.qc.reserve(r.nqc + 1)); CK(r.ts.reserve(r.nts + 1)); CK(r.tc.reserve(r.ntc + 1));
+  CK(r.qs_off.reserve(n + 1)); CK(r.qc_off.reserve(n + 1)); CK(r.ts_off.reserve(n + 1)); CK(r.tc_off.reserve(n + 1));
+  CK(r.state_in.reserve((size_t)n * 20)); CK(r.cov_in.reserve((size_t)n * 324));
+  // pack 32-B PointXYZI -> 16-B float4 while copying into pinned staging (the copy is needed anyway: user
+  // buffers are pageable), so PCIe moves half the bytes
+  float4* hp = r.h_pts.p;
+  size_t seg[5] = {0, r.nqs, r.nqs + r.nqc, r.nqs + r.nqc + r.nts, total};
+  for (int k = 0; k < 4; ++k) pack_into(hp + seg[k], pts[k], (int)(seg[k + 1] - seg[k]));
+  for (int k = 0; k < 4; ++k) std::memcpy(r.h_off.p + (size_t)k * (n + 1), offs[k], sizeof(int) * (n + 1));
+  for (int i = 0; i < n; ++i) {
+    std::memcpy(r.h_state.p + (size_t)i * 20, b->state_in + (size_t)i * 19, sizeof(double) * 19);
+    r.h_state.p[(size_t)i * 20 + 19] = 0.0;
+  }
+  std::memcpy(r.h_cov.p, b->cov_in, sizeof(double) * 324 * (size_t)n);
+  float4* dsts[4] = {r.qs.p, r.qc.p, r.ts.p, r.tc.p};
+  int* doffs[4] = {r.qs_off.p, r.qc_off.p, r.ts_off.p, r.tc_off.p};
+  for (int k = 0; k < 4; ++k) {
+    size_t cnt = seg[k + 1] - seg[k];
+    if (cnt) CK(cudaMemcpyAsync(dsts[k], hp + seg[k], sizeof(float4) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(doffs[k], r.h_off.p + (size_t)k * (n + 1), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CK(cudaMemcpyAsync(r.state_in.p, r.h_state.p, sizeof(double) * 20 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(r.cov_in.p, r.h_cov.p, sizeof(double) * 324 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  return reserve_outputs(ctx, r, true, false);
+}
+
+int lins_gpu_batch_run(lins_ctx* ctx) {
+  if (!ctx) return LINS_E_INVALID;
+  Resident& r = ctx->batch;
+  if (r.n <= 0) return fail(ctx, LINS_E_INVALID, "no resident batch");
+  CK(cudaSetDevice(ctx->device));
+  BatchView bv = view_of(r, true, false);
+  return launch(ctx, bv, make_kparams(ctx->prm, MODE_IESKF, 0));
+}
+
+int lins_gpu_batch_download(lins_ctx* ctx, double* state_out, double* cov_out, lins_scan_result* results,
+                            lins_report* reports) {
+  if (!ctx) return LINS_E_INVALID;
+  Resident& r = ctx->batch;
+  if (r.n <= 0) return fail(ctx, LINS_E_INVALID, "no resident batch");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = r.n;
+  if (state_out) { CK(r.h_state_out.reserve(n * 20)); CK(cudaMemcpyAsync(r.h_state_out.p, r.state_out.p, sizeof(double) * 20 * n, cudaMemcpyDeviceToHost, ctx->stream)); }
+  if (cov_out) { CK(r.h_cov_out.reserve(n * 324)); CK(cudaMemcpyAsync(r.h_cov_out.p, r.cov_out.p, sizeof(double) * 324 * n, cudaMemcpyDeviceToHost, ctx->stream)); }
+  if (results) { CK(r.h_results.reserve(n)); CK(cudaMemcpyAsync(r.h_results.p, r.results.p, sizeof(lins_scan_result) * n, cudaMemcpyDeviceToHost, ctx->stream)); }
+  if (reports) { CK(r.h_reports.reserve(n)); CK(cudaMemcpyAsync(r.h_reports.p, r.reports.p, sizeof(lins_report) * n, cudaMemcpyDeviceToHost, ctx->stream)); }
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (state_out) for (size_t i = 0; i < n; ++i) std::memcpy(state_out + i * 19, r.h_state_out.p + i * 20, sizeof(double) * 19);
+  if (cov_out) std::memcpy(cov_out, r.h_cov_out.p, sizeof(double) * 324 * n);
+  if (results) std::memcpy(results, r.h_results.p, sizeof(lins_scan_result) * n);
+  if (reports) std::memcpy(reports, r.h_reports.p, sizeof(lins_report) * n);
+  return LINS_OK;
+}
+
+int lins_gpu_ieskf_batch(lins_ctx* ctx, const lins_batch_desc* batch, double* state_out, double* cov_out,
+                         lins_scan_result* results) {
+  int rc = lins_gpu_batch_upload(ctx, batch);
+  if (rc != LINS_OK) return rc;
+  if (batch->n_scans == 0) return LINS_OK;
+  rc = lins_gpu_batch_run(ctx);
+  if (rc != LINS_OK) return rc;
+  return lins_gpu_batch_download(ctx, state_out, cov_out, results, nullptr);
+}
+
+int lins_gpu_batch_results_device(lins_ctx* ctx, void** dev_ptr, int* n_scans) {
+  if (!ctx || !dev_ptr) return LINS_E_INVALID;
+  *dev_ptr = ctx->batch.results.p;
+  if (n_scans) *n_scans = ctx->batch.n;
+  return LINS_OK;
+}
+
+int lins_gpu_sync(lins_ctx* ctx) {
+  if (!ctx) return LINS_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return LINS_OK;
+}
+
+}  // extern "C"
