@@ -6,10 +6,13 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <new>
 #include <string>
 #include <vector>
 
+#include "../host/math_utils.hpp"
+#include "../host/small_linalg.hpp"
 #include "lins_kernels.cuh"
 
 using namespace lins_dev;
@@ -188,6 +191,74 @@ __global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_const
       if (rep) { rep->iters = iters; rep->converged = sm.flags[0]; rep->diverged = sm.flags[1]; rep->has_nan = sm.flags[2]; }
     }
     __syncthreads();
+  }
+}
+
+
+// Split "Jacobian kernel" (SURVEY.md §8(d) unit U1; rows A5-A9 form B given the correspondence IDs).
+// One warp per scan: streams the scan's queries (16 B each, coalesced) and IDs (12 / 8 B, coalesced), gathers
+// the 3 / 2 matched targets (16 B each), recomputes de-skew, residual, weight and Jacobian row, and reduces
+// the 28 sums per scan with a fixed shuffle tree.  Nothing is staged in shared memory: with >= 4096 resident
+// scans the working set exceeds L2 and the kernel is bound by HBM traffic + f64 issue.
+__global__ void __launch_bounds__(kThreads) lins_jacobian_kernel(const __grid_constant__ BatchView bv,
+                                                                 const __grid_constant__ KParams kp) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * kThreads) >> 5;
+  for (int scan = (blockIdx.x * kThreads + threadIdx.x) >> 5; scan < bv.n_scans; scan += warps_per_grid) {
+    // per-scan constants (every lane computes the same values)
+    const double* st = bv.state_in + (size_t)scan * 20;
+    double rn[3] = {st[0], st[1], st[2]};
+    q4 q; q.x = st[6]; q.y = st[7]; q.z = st[8]; q.w = st[9];
+    const d3 phi = Quat2axis(q);
+    const m3 R = qtoR(q);
+    const int qs0 = bv.qs_off[scan], ns = bv.qs_off[scan + 1] - qs0;
+    const int qc0 = bv.qc_off[scan], nc = bv.qc_off[scan + 1] - qc0;
+    const float4* __restrict__ tgtS = bv.ts + bv.ts_off[scan];
+    const float4* __restrict__ tgtC = bv.tc + bv.tc_off[scan];
+    const int Ts = bv.ts_off[scan + 1] - bv.ts_off[scan], Tc = bv.tc_off[scan + 1] - bv.tc_off[scan];
+    double acc[kNAcc];
+#pragma unroll
+    for (int k = 0; k < kNAcc; ++k) acc[k] = 0.0;
+    int cs = 0, cc = 0;
+    const bool weighted = kp.iter0 >= kp.icp_freq;
+    for (int i = lane; i < ns + nc; i += 32) {
+      const bool surf = i < ns;
+      const float4 p = surf ? __ldg(bv.qs + qs0 + i) : __ldg(bv.qc + qc0 + (i - ns));
+      // A2 de-skew
+      float fi = p.w - (float)((int)p.w);
+      double s = (1.f / kp.scan_period) * fi;
+      q4 rq = axis2Quat(mk3(s * phi.x, s * phi.y, s * phi.z));
+      d3 rp = qrot(rq, mk3(p.x, p.y, p.z));
+      float4 sel;
+      sel.x = (float)(rp.x + s * rn[0]); sel.y = (float)(rp.y + s * rn[1]); sel.z = (float)(rp.z + s * rn[2]); sel.w = p.w;
+      float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool ok = false;
+      if (surf) {
+        const int* id = bv.ind_s + 3 * (size_t)(qs0 + i);
+        const int i1 = __ldg(id), i2 = __ldg(id + 1), i3 = __ldg(id + 2);
+        if (i2 >= 0 && i3 >= 0 && i1 >= 0 && i1 < Ts && i2 < Ts && i3 < Ts)
+          ok = plane_residual(sel, __ldg(&tgtS[i1]), __ldg(&tgtS[i2]), __ldg(&tgtS[i3]), weighted, coeff);
+      } else {
+        const int* id = bv.ind_c + 2 * (size_t)(qc0 + (i - ns));
+        const int i1 = __ldg(id), i2 = __ldg(id + 1);
+        if (i2 >= 0 && i1 >= 0 && i1 < Tc && i2 < Tc) ok = line_residual(sel, __ldg(&tgtC[i1]), __ldg(&tgtC[i2]), weighted, coeff);
+      }
+      if (ok) {
+        accumulate_row(p, coeff, R.m, kp.lidar_scale, acc);
+        if (surf) ++cs; else ++cc;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kNAcc; ++k) {
+      double v = acc[k];
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if (lane == (k & 31)) bv.accum[(size_t)scan * 32 + k] = v;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) { cs += __shfl_xor_sync(0xffffffffu, cs, m); cc += __shfl_xor_sync(0xffffffffu, cc, m); }
+    if (lane == 28) bv.accum[(size_t)scan * 32 + 28] = (double)cs;
+    if (lane == 29) bv.accum[(size_t)scan * 32 + 29] = (double)cc;
   }
 }
 
@@ -683,6 +754,140 @@ int lins_gpu_sync(lins_ctx* ctx) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   return LINS_OK;
+}
+
+
+int lins_gpu_batch_jacobian_pass(lins_ctx* ctx, double* accum_out) {
+  if (!ctx) return LINS_E_INVALID;
+  Resident& r = ctx->batch;
+  if (r.n <= 0) return fail(ctx, LINS_E_INVALID, "no resident batch");
+  CK(cudaSetDevice(ctx->device));
+  BatchView bv = view_of(r, false, false);
+  bv.state_in = r.state_out.p;  // linearise at the updated state; IDs = the last iteration's
+  KParams kp = make_kparams(ctx->prm, MODE_JACOBIAN, 1);
+  const int warps_needed = r.n;
+  int grid = std::min((warps_needed + kWarps - 1) / kWarps, ctx->sm_count * 8);
+  if (grid < 1) grid = 1;
+  lins_jacobian_kernel<<<grid, kThreads, 0, ctx->stream>>>(bv, kp);
+  CK(cudaGetLastError());
+  ctx->launches += 1;
+  if (accum_out) {
+    CK(r.h_accum.reserve((size_t)r.n * 32));
+    CK(cudaMemcpyAsync(r.h_accum.p, r.accum.p, sizeof(double) * 32 * (size_t)r.n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(accum_out, r.h_accum.p, sizeof(double) * 32 * (size_t)r.n);
+  }
+  return LINS_OK;
+}
+
+// ≙ estimateTransform (StateEstimator.hpp:1163-1196): the association + J^T J / J^T b reduction of every
+// Gauss-Newton step runs on device (MODE_ICP_REDUCE); the 6x6 solve / degeneracy projection / pose update of
+// calculateTransformation (:1260-1320) run on the host (rare fallback path: one small D2H per step).
+int lins_gpu_estimate_transform(lins_ctx* ctx, const lins_point* surf_flat, int ns, const lins_point* corner_sharp,
+                                int nc, double* pose_io, int* iters_out, int* converged_out) {
+  if (!ctx) return LINS_E_INVALID;
+  if (!pose_io) return fail(ctx, LINS_E_INVALID, "null pose");
+  CK(cudaSetDevice(ctx->device));
+  using namespace lins;
+  V3D t(pose_io[0], pose_io[1], pose_io[2]);
+  Q4D q(pose_io[6], pose_io[3], pose_io[4], pose_io[5]);
+  double lin[19];
+  std::memset(lin, 0, sizeof(lin));
+  linalg::Mat<6> matP{};
+  bool conv = false;
+  int it = 0;
+  Resident& r = ctx->single;
+  for (int iter = 0; iter < ctx->prm.num_iter; ++iter) {
+    it = iter + 1;
+    lin[0] = t.x(); lin[1] = t.y(); lin[2] = t.z();
+    lin[6] = q.x(); lin[7] = q.y(); lin[8] = q.z(); lin[9] = q.w();
+    int rc = stage_single(ctx, surf_flat, ns, corner_sharp, nc, lin, nullptr, false);
+    if (rc != LINS_OK) return rc;
+    BatchView bv = single_view(ctx, false);
+    rc = launch(ctx, bv, make_kparams(ctx->prm, MODE_ICP_REDUCE, iter));
+    if (rc != LINS_OK) return rc;
+    CK(r.h_accum.reserve(32));
+    CK(cudaMemcpyAsync(r.h_accum.p, r.accum.p, sizeof(double) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const double* a = r.h_accum.p;
+    if (a[28] < 10) continue;  // "Insufficient matched surfs..." (:1175-1178)
+    if (a[29] < 5) continue;   // "Insufficient matched corners..." (:1181-1184)
+    linalg::Mat<6> JTJ;
+    linalg::Vec<6> JTb;
+    int k = 0;
+    for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { JTJ[i][j] = a[k]; JTJ[j][i] = a[k]; ++k; }
+    for (int i = 0; i < 6; ++i) JTb[i] = a[21 + i];
+    linalg::Vec<6> x = linalg::colPivQrSolve<6>(JTJ, JTb);
+    bool isDegenerate = false;
+    if (iter == 0) {  // :1269-1296
+      linalg::Vec<6> matE;
+      linalg::Mat<6> matV, matV2, Vinv;
+      linalg::symmetricEigen<6>(JTJ, matE, matV);
+      matV2 = matV;
+      for (int i = 0; i < 6; ++i) {
+        if (matE[i] < 10.) { for (int j = 0; j < 6; ++j) matV2[i][j] = 0; isDegenerate = true; }
+        else break;
+      }
+      if (!linalg::inverse<6>(matV, Vinv)) for (auto& row : Vinv) for (auto& e : row) e = std::numeric_limits<double>::quiet_NaN();
+      for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double sacc = 0; for (int m = 0; m < 6; ++m) sacc += Vinv[i][m] * matV2[m][j]; matP[i][j] = sacc; }
+    }
+    if (isDegenerate) {
+      linalg::Vec<6> x2 = x;
+      for (int i = 0; i < 6; ++i) { double sacc = 0; for (int j = 0; j < 6; ++j) sacc += matP[i][j] * x2[j]; x[i] = sacc; }
+    }
+    Q4D dq = math_utils::rpy2Quat(V3D(x[0], x[1], x[2]));
+    q = (q * dq).normalized();
+    t = t + V3D(x[3], x[4], x[5]);
+    double deltaR = V3D(math_utils::rad2deg(x[0]), math_utils::rad2deg(x[1]), math_utils::rad2deg(x[2])).norm();
+    double deltaT = V3D(100 * x[3], 100 * x[4], 100 * x[5]).norm();
+    if (deltaR < 0.1 && deltaT < 0.1) { conv = true; break; }
+  }
+  pose_io[0] = t.x(); pose_io[1] = t.y(); pose_io[2] = t.z();
+  pose_io[3] = q.x(); pose_io[4] = q.y(); pose_io[5] = q.z(); pose_io[6] = q.w();
+  if (iters_out) *iters_out = it;
+  if (converged_out) *converged_out = conv ? 1 : 0;
+  return LINS_OK;
+}
+
+// ≙ updatePointCloud (StateEstimator.hpp:1116-1161), XYZ part: transformToEnd on device, results copied back
+// into the caller's clouds (the reference transforms scan_new_'s clouds in place), then the map swap + the
+// guarded index refresh.
+int lins_gpu_update_map(lins_ctx* ctx, lins_point* surf, int ns, lins_point* corner, int nc, const double* lin_state,
+                        int* map_replaced) {
+  if (!ctx) return LINS_E_INVALID;
+  if (ns < 0 || nc < 0 || (ns > 0 && !surf) || (nc > 0 && !corner) || !lin_state) return fail(ctx, LINS_E_INVALID, "bad update_map args");
+  CK(cudaSetDevice(ctx->device));
+  const bool rebuild = nc >= 5 && ns >= 20;  // :1156-1157
+  // keep the old map alive as the 1-NN cloud if the guard fails
+  if (!rebuild && ctx->tree_is_map) {
+    std::swap(ctx->tree_s, ctx->map_s); std::swap(ctx->tree_c, ctx->map_c);
+    ctx->tree_ns = std::max(ctx->map_ns, 0); ctx->tree_nc = std::max(ctx->map_nc, 0);
+    ctx->tree_is_map = false;
+  }
+  CK(ctx->map_s.reserve(ns + 1)); CK(ctx->map_c.reserve(nc + 1));
+  CK(ctx->tree_s.reserve(1)); CK(ctx->tree_c.reserve(1));
+  CK(ctx->h_tmp.reserve((size_t)ns + nc + 1));
+  CK(ctx->tmp_lin.reserve(20));
+  pack_into(ctx->h_tmp.p, surf, ns);
+  pack_into(ctx->h_tmp.p + ns, corner, nc);
+  double lin[20];
+  std::memcpy(lin, lin_state, sizeof(double) * 19);
+  lin[19] = 0;
+  CK(cudaMemcpyAsync(ctx->tmp_lin.p, lin, sizeof(lin), cudaMemcpyHostToDevice, ctx->stream));
+  if (ns) CK(cudaMemcpyAsync(ctx->map_s.p, ctx->h_tmp.p, sizeof(float4) * ns, cudaMemcpyHostToDevice, ctx->stream));
+  if (nc) CK(cudaMemcpyAsync(ctx->map_c.p, ctx->h_tmp.p + ns, sizeof(float4) * nc, cudaMemcpyHostToDevice, ctx->stream));
+  if (ns) { lins_transform_to_end_kernel<<<(ns + 255) / 256, 256, 0, ctx->stream>>>(ctx->map_s.p, ns, ctx->tmp_lin.p, ctx->prm.scan_period); ctx->launches += 1; }
+  if (nc) { lins_transform_to_end_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(ctx->map_c.p, nc, ctx->tmp_lin.p, ctx->prm.scan_period); ctx->launches += 1; }
+  CK(cudaGetLastError());
+  if (ns) CK(cudaMemcpyAsync(ctx->h_tmp.p, ctx->map_s.p, sizeof(float4) * ns, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nc) CK(cudaMemcpyAsync(ctx->h_tmp.p + ns, ctx->map_c.p, sizeof(float4) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < ns; ++i) { surf[i].x = ctx->h_tmp.p[i].x; surf[i].y = ctx->h_tmp.p[i].y; surf[i].z = ctx->h_tmp.p[i].z; }
+  for (int i = 0; i < nc; ++i) { corner[i].x = ctx->h_tmp.p[ns + i].x; corner[i].y = ctx->h_tmp.p[ns + i].y; corner[i].z = ctx->h_tmp.p[ns + i].z; }
+  ctx->map_ns = ns; ctx->map_nc = nc;
+  if (rebuild) { ctx->tree_is_map = true; ctx->tree_ns = ns; ctx->tree_nc = nc; }
+  if (map_replaced) *map_replaced = rebuild ? 1 : 0;
+  return upload_map_offsets(ctx);
 }
 
 }  // extern "C"

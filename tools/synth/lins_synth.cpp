@@ -51,6 +51,7 @@ struct Pole { double cx, cy, r; };
 struct Box { double x0, x1, y0, y1, h; };
 struct World {
   double Lx = 20, Ly = 15;  // walls at x = +-Lx, y = +-Ly
+  bool walls = true;
   std::vector<Pole> poles;
   std::vector<Box> boxes;
 };
@@ -66,14 +67,16 @@ World make_world(Rng& rng, int kind) {
       double cx = rng.uni(-w.Lx + 3, w.Lx - 3), cy = rng.uni(-w.Ly + 3, w.Ly - 3), sx = rng.uni(0.5, 2.0), sy = rng.uni(0.5, 2.0);
       w.boxes.push_back(Box{cx - sx, cx + sx, cy - sy, cy + sy, rng.uni(0.8, 3.0)});
     }
-  } else {  // open flat ground, sparse poles, distant walls
-    w.Lx = rng.uni(45, 60); w.Ly = rng.uni(45, 60);
-    int np = 14 + (int)(rng.uni() * 8);
+  } else {  // open flat ground, sparse poles, a few buildings; no enclosing walls (sky = no return)
+    w.walls = false;
+    w.Lx = w.Ly = 1e9;
+    int np = 16 + (int)(rng.uni() * 10);
     for (int i = 0; i < np; ++i) w.poles.push_back(Pole{rng.uni(-30, 30), rng.uni(-30, 30), rng.uni(0.15, 0.4)});
-    int nb = 2 + (int)(rng.uni() * 3);
+    int nb = 5 + (int)(rng.uni() * 4);
     for (int i = 0; i < nb; ++i) {
-      double cx = rng.uni(-25, 25), cy = rng.uni(-25, 25), sx = rng.uni(0.8, 3.0), sy = rng.uni(0.8, 3.0);
-      w.boxes.push_back(Box{cx - sx, cx + sx, cy - sy, cy + sy, rng.uni(1.0, 4.0)});
+      double cx = rng.uni(-35, 35), cy = rng.uni(-35, 35), sx = rng.uni(1.0, 6.0), sy = rng.uni(1.0, 6.0);
+      if (std::fabs(cx) < 12 && std::fabs(cy) < 12) { cx += cx >= 0 ? 14 : -14; }  // keep the sensor's start area free
+      w.boxes.push_back(Box{cx - sx, cx + sx, cy - sy, cy + sy, rng.uni(2.0, 8.0)});
     }
   }
   return w;
@@ -84,8 +87,10 @@ double raycast(const World& w, const V3D& o, const V3D& d) {
   double best = INFINITY;
   auto upd = [&](double t) { if (t > 0.3 && t < best) best = t; };
   if (d.z() < -1e-12) upd(-o.z() / d.z());  // ground z = 0
-  if (d.x() > 1e-12) upd((w.Lx - o.x()) / d.x()); else if (d.x() < -1e-12) upd((-w.Lx - o.x()) / d.x());
-  if (d.y() > 1e-12) upd((w.Ly - o.y()) / d.y()); else if (d.y() < -1e-12) upd((-w.Ly - o.y()) / d.y());
+  if (w.walls) {
+    if (d.x() > 1e-12) upd((w.Lx - o.x()) / d.x()); else if (d.x() < -1e-12) upd((-w.Lx - o.x()) / d.x());
+    if (d.y() > 1e-12) upd((w.Ly - o.y()) / d.y()); else if (d.y() < -1e-12) upd((-w.Ly - o.y()) / d.y());
+  }
   const double a = d.x() * d.x() + d.y() * d.y();
   if (a > 1e-12) {
     for (const auto& p : w.poles) {
