@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — ESKF iterations / second of the B200-native LINS IESKF update path.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W [--impl reference]`.
+  * workload: BASELINE.json configs[2] "synthetic 1000-scan sequence, flat-ground map" — 1000 independent
+    (scan pair, prior) units per GPU (configs[1], the real bag, is not available: no dataset, no network);
+    a STEP = one pass of the whole iterated update (performIESKF, all iterations) over the 1000 resident units.
+  * value  = ESKF iterations executed by all ranks per second, inputs already resident in HBM (device-timed
+    with CUDA events on the launching stream, max over ranks); one fused kernel launch per step.
+  * e2e    = the same metric through the reference-facing C-ABI call lins_gpu_ieskf_batch with HOST buffers
+    (pack + H2D + kernel + D2H inside the timed region).
+  * roofline = dominant kernel (the fused IESKF kernel): algorithmic bytes per launch / its average duration
+    against MEASURED_PEAKS.json hbm_gbs;  roofline_jacobian = the split Jacobian kernel.
+  * cpu_baseline = the CPU oracle (a port of the reference path: it cannot be compiled here) in the
+    reference-faithful M x M form, on the box's host cores, on a bounded sample of the same workload.
+  * --impl reference: the same oracle arm timed alone (rank 0 only under torchrun).
+L2 hygiene: three different 1000-unit batches (3 x ~87 MB > 126 MB L2) are resident and used round-robin, so
+no step finds its inputs in L2.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SCANS_PER_GPU = 1000
+WORKLOAD = "config3: synthetic 1000-scan flat-ground sequence (BASELINE.json configs[2]), 16x1800 VLP-16, shipped exp_port.yaml params (num_iter 30)"
+
+
+def pkg(name):
+    return importlib.import_module("lins---lidar-inertial-slam_b200." + name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def algorithmic_bytes(batch, iters):
+    """Compulsory HBM bytes of one fused launch over `batch`: every query / target point
+    once per scan (16 B packed), prior in, posterior out, the correspondence IDs written every iteration
+    (`iters` = per-scan iteration counts)."""
+    ns = np.diff(batch.offsets["surf_flat"]).astype(np.int64)
+    nc = np.diff(batch.offsets["corner_sharp"]).astype(np.int64)
+    ts = np.diff(batch.offsets["surf_less_flat"]).astype(np.int64)
+    tc = np.diff(batch.offsets["corner_less_sharp"]).astype(np.int64)
+    per_scan = 16 * (ns + nc + ts + tc) + (20 + 324) * 8 + (20 + 324) * 8 + 64 + 4 * (3 * ns + 2 * nc) * np.asarray(iters, np.int64)
+    return int(per_scan.sum())
+
+
+def jacobian_bytes(batch):
+    """76 B per surf query + 56 B per corner query + 384 B per scan."""
+    ns = int(batch.offsets["surf_flat"][-1]); nc = int(batch.offsets["corner_sharp"][-1])
+    return 76 * ns + 56 * nc + 384 * batch.n
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the CPU oracle (port of the reference path; the reference itself needs ROS/PCL/Eigen and
+    cannot be built here), reference-faithful M x M gain, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import oracle_binding as ob
+    synth = pkg("synth")
+    cores = os.cpu_count() or 1
+    sample = max(cores, min(96, 12 * cores))
+    b = synth.generate("config3", n=sample, seed0=1000)
+    prm = ob.LinsParams.shipped()
+    for _ in range(max(1, min(args.warmup, 1))):
+        ob.ieskf_batch(prm, b, count=min(sample, cores), form=ob.FORM_A, threads=cores, want_cov=False)
+    tot_it, tot_s = 0, 0.0
+    for _ in range(args.steps):
+        _, _, _, sec, its = ob.ieskf_batch(prm, b, form=ob.FORM_A, threads=cores, want_cov=True)
+        tot_it += its; tot_s += sec
+    val = tot_it / tot_s
+    out = {
+        "impl": "reference", "metric": "ESKF iterations/sec", "value": val, "unit": "iterations/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 (f32 association)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{sample} of the 1000 scans per step, seeds 1000..{1000 + sample - 1}"},
+        "cpu_baseline": {"value": val, "unit": "iterations/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} scans x {args.steps} steps, reference-faithful MxM Kalman gain (StateEstimator.hpp:542-546), kd-tree 1-NN, scan-parallel std::thread"},
+        "e2e": {"value": val, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scans", type=int, default=SCANS_PER_GPU, help="units per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    capi, synth, defs = pkg("capi"), pkg("synth"), pkg("ctypes_defs")
+    prm = defs.LinsParams.shipped()
+    # a non-default torch stream: its handle is non-NULL, so the library launches on it (NULL would make the
+    # library create its own stream and torch.cuda.Event would not see the kernels)
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+
+    # ---- inputs: 3 resident batches of `scans` units each; weak scaling = different seeds per rank ----------
+    NB = 3
+    n = args.scans
+    batches = [synth.generate("config3", n=n, seed0=1000 + 100000 * rank + 10000 * k) for k in range(NB)]
+    ctxs = [capi.LinsGpu(prm, device=local, stream=stream.cuda_stream) for _ in range(NB)]
+    for c, b in zip(ctxs, batches):
+        c.batch_upload(b)
+    torch.cuda.synchronize()
+
+    class _DevView:  # zero-copy torch view of the resident result records (64 B / scan)
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    res_views = []
+    for c in ctxs:
+        p, nn = c.batch_results_device()
+        res_views.append(torch.as_tensor(_DevView(p, nn * 64), device=f"cuda:{local}"))
+    gathered = torch.empty(world * n * 64, dtype=torch.uint8, device=f"cuda:{local}") if world > 1 else None
+
+    def step(k):
+        c = ctxs[k % NB]
+        c.batch_run()  # one fused kernel launch on torch's current stream
+        if world > 1:  # the path's only exchange: the pose gather (64 B / scan)
+            dist.all_gather_into_tensor(gathered, res_views[k % NB])
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    iters_per_batch, iters_per_scan = [], []
+    for c in ctxs:
+        _, _, res, _ = c.batch_download(states=False, covs=False)
+        iters_per_batch.append(int(res["iters"].sum()))
+        iters_per_scan.append(res["iters"].astype(np.int64))
+
+    # ---- timed region: exactly K steps ----------------------------------------------------------------------
+    launches0 = sum(c.launch_count() for c in ctxs)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        ctxs[k % NB].batch_run()
+        ev[k][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, res_views[k % NB])
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clk = clocks.stop() if rank == 0 else None
+    elapsed_ms = e0.elapsed_time(e1)
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    launches = sum(c.launch_count() for c in ctxs) - launches0
+    my_iters = sum(iters_per_batch[k % NB] for k in range(args.steps))
+    t = torch.tensor([elapsed_ms, float(my_iters), float(launches)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, total_iters, total_launches = float(tmax[0]), float(tsum[1]), int(tsum[2])
+    else:
+        total_iters, total_launches = float(my_iters), launches
+    value = total_iters / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the C-ABI with host buffers (pack + H2D + kernel + D2H timed) ------------------------
+    e2e_ctx = ctxs[0]
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ctx.ieskf_batch(batches[0])  # warm
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for k in range(e2e_steps):
+        _, _, res = e2e_ctx.ieskf_batch(batches[k % NB])
+        e2e_iters += int(res["iters"].sum())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, float(e2e_iters)], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        s = te.clone(); dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        e2e_s, e2e_iters = float(a[0]), float(s[1])
+    b0 = batches[0]
+    pts = sum(int(b0.offsets[k][-1]) for k in b0.FIELDS)
+    h2d = 16 * pts + 4 * 4 * (n + 1) + n * (20 + 324) * 8
+    d2h = n * ((20 + 324) * 8 + 64)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel + the split Jacobian kernel (rank 0, N-independent) ----------------------
+    peak, peak_src = measured_peak()
+    alg = float(np.mean([algorithmic_bytes(batches[k % NB], iters_per_scan[k % NB]) for k in range(args.steps)]))
+    kms = float(np.mean(kernel_ms))
+    achieved = alg / (kms * 1e-3) / 1e9
+    roofline = {"kernel": "lins_ieskf_kernel<MODE_IESKF> (fused de-skew + 1-NN + ring walks + residual/Jacobian fold + 18x18 solve, all iterations)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": kms,
+                "note": "latency/issue bound by design: per scan ~90 KB of compulsory bytes feed ~10^7 f32 distance evaluations served from L1/L2; see DESIGN.md"}
+    # Jacobian kernel: tile the resident batch past L2 and time the split kernel alone
+    jb = batches[0].tile(5)
+    jctx = capi.LinsGpu(prm, device=local, stream=stream.cuda_stream)
+    jctx.batch_upload(jb); jctx.batch_run(); torch.cuda.synchronize()
+    for _ in range(3):
+        jctx.batch_jacobian_pass()
+    torch.cuda.synchronize()
+    ja, jb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    ja.record()
+    for _ in range(reps):
+        jctx.batch_jacobian_pass()
+    jb_.record(); torch.cuda.synchronize()
+    jms = ja.elapsed_time(jb_) / reps
+    jbytes = jacobian_bytes(jb)
+    roofline_j = {"kernel": "lins_jacobian_kernel (SURVEY.md §8(d) unit U1, given correspondence IDs)", "bound": "hbm", "achieved": jbytes / (jms * 1e-3) / 1e9,
+                  "peak": peak, "unit": "GB/s", "frac": jbytes / (jms * 1e-3) / 1e9 / peak, "traffic": None, "scans": jb.n, "avg_launch_ms": jms,
+                  "algorithmic_bytes_per_launch": jbytes, "working_set_mb": (16 * sum(int(jb.offsets[k][-1]) for k in jb.FIELDS)) / 1e6}
+    jctx.close()
+
+    # ---- CPU baseline (rank 0, N = 1 only): oracle on the host cores, bounded sample ---------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle_binding as ob
+        cores = os.cpu_count() or 1
+        sample = max(cores, min(96, 12 * cores))
+        _, _, _, secA, itsA = ob.ieskf_batch(prm, batches[0], count=sample, form=ob.FORM_A, threads=cores, want_cov=True)
+        _, _, _, secB1, itsB1 = ob.ieskf_batch(prm, batches[0], count=min(n, 4 * sample), form=ob.FORM_B, threads=1, want_cov=True)
+        _, _, _, secBn, itsBn = ob.ieskf_batch(prm, batches[0], count=n, form=ob.FORM_B, threads=cores, want_cov=True)
+        cpu = {"value": itsA / secA, "unit": "iterations/s", "cores": cores, "kind": "port",
+               "sample": f"first {sample} scans of batch 0; reference-faithful MxM gain (form A), kd-tree 1-NN, {cores} scan-parallel threads",
+               "form_b_18x18_1thread_iters_per_s": itsB1 / secB1, "form_b_18x18_allcores_iters_per_s": itsBn / secBn}
+
+    out = {
+        "metric": "ESKF iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 (f32 association)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "scans_per_gpu_per_step": n, "iterations_per_step_rank0": float(np.mean(iters_per_batch)),
+                   "l2": f"{NB} resident batches used round-robin ({NB} x {h2d / 1e6:.0f} MB > 126 MB L2)", "parallelism": f"scan-sharded x{world}, pose all_gather per step" if world > 1 else "1 GPU"},
+        "clocks": clk,
+        "e2e": {"value": e2e_iters / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "gpu_launches": int(total_launches),
+        "roofline": roofline, "roofline_jacobian": roofline_j,
+    }
+    if cpu:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

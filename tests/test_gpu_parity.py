@@ -294,11 +294,11 @@ def test_jacobian_pass_matches_fused_reduction(gpu, ob, golden_batch):
         o = ob.Oracle(prm1)
         o.set_map(u["surf_less_flat"], u["corner_less_sharp"])
         o.associate(u["surf_flat"], u["corner_sharp"], u["state"], 0)  # IDs at the prior (what iteration 0 stored)
-        # weights/coeffs of "iter 1" at the updated state with those stored IDs: icp_freq=2 makes iter 1 reuse them
+        # weights/coeffs at the updated state with those stored IDs: with icp_freq=2, iteration 3 reuses them
         o2 = ob.Oracle(ob.LinsParams.shipped(icp_freq=2), use_kdtree=False)
         o2.set_map(u["surf_less_flat"], u["corner_less_sharp"])
         o2.associate(u["surf_flat"], u["corner_sharp"], u["state"], 0)
-        a1 = o2.associate(u["surf_flat"], u["corner_sharp"], so[i], 1)
+        a1 = o2.associate(u["surf_flat"], u["corner_sharp"], so[i], 3)  # 3 % 2 != 0: reuse IDs; 3 >= 2: weighted
         kp = np.concatenate([u["surf_flat"][a1["surf_mask"] == 1], u["corner_sharp"][a1["corner_mask"] == 1]])
         cf = np.concatenate([a1["surf_coeff"][a1["surf_mask"] == 1], a1["corner_coeff"][a1["corner_mask"] == 1]])
         n = len(kp)
