@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <limits>
@@ -68,6 +70,13 @@ __global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_const
       const int tc0 = bv.tc_off[scan], Tc = bv.tc_off[scan + 1] - tc0;
       build_ring_table(bv.ts + ts0, Ts, sm.rsS, &sm.sortedS);
       build_ring_table(bv.tc + tc0, Tc, sm.rsC, &sm.sortedC);
+      // the exact 1-NN index (≙ kdtree*->setInputCloud, StateEstimator.hpp:363-364 / :1158-1159), on device
+      const float4* nnS = bv.nn_s ? bv.nn_s + bv.nn_s_off[scan] : bv.ts + ts0;
+      const float4* nnC = bv.nn_c ? bv.nn_c + bv.nn_c_off[scan] : bv.tc + tc0;
+      const int TnS = bv.nn_s ? bv.nn_s_off[scan + 1] - bv.nn_s_off[scan] : Ts;
+      const int TnC = bv.nn_c ? bv.nn_c_off[scan + 1] - bv.nn_c_off[scan] : Tc;
+      grid_build<kHashS>(nnS, TnS, bv.grid_s + (bv.nn_s ? bv.nn_s_off[scan] : ts0), sm.bstartS, sm.scan_tmp);
+      grid_build<kHashC>(nnC, TnC, bv.grid_c + (bv.nn_c ? bv.nn_c_off[scan] : tc0), sm.bstartC, sm.scan_tmp);
     }
     lins_report* rep = bv.reports ? bv.reports + scan : nullptr;
     int iters = 0;
@@ -92,25 +101,26 @@ __global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_const
       build_A6(sm);
       if (tid == 128) box_minus(sm);
       __syncthreads();
-      if (tid < 6) {  // y = b + A d on the 6 structural rows
-        double s = sm.y6[tid];
-        for (int c = 0; c < 6; ++c) s += sm.A6[tid * 6 + c] * sm.dvec[col6(c)];
-        sm.y6[tid] = s;
-      }
-      form_S(sm, sig2);
-      __syncthreads();
-      if (tid < 18) {  // rhs = P y
-        double s = 0;
-        for (int c = 0; c < 6; ++c) s += sm.P[tid * 18 + col6(c)] * sm.y6[c];
-        sm.B[tid] = s;
-      }
-      __syncthreads();
       if (warp == 0) {
-        const bool ok = warp_lu_solve(sm.S, sm.B, 1);
+        if (lane < 6) {  // y = b6 + A6 d_c on the 6 structural rows
+          double y = sm.y6[lane];
+          for (int c = 0; c < 6; ++c) y += sm.A6[lane * 6 + c] * sm.dvec[col6(c)];
+          sm.X6[lane] = y;
+        }
+        form_M6(sm, sig2, lane, 32);
+        __syncwarp();
+        const bool ok = warp_lu_solve<6>(sm.M6, sm.X6, 1);  // z = M^-1 (b6 + A6 d_c)
+        __syncwarp();
+        if (lane < 18) {  // K (r + H d) = P[:,c] z
+          double kx = 0;
+          for (int c = 0; c < 6; ++c) kx += sm.P[lane * 18 + col6(c)] * sm.X6[c];
+          sm.upd[lane] = ok ? (-kx + sm.dvec[lane]) : __longlong_as_double(0x7ff8000000000000ll);
+        }
+        __syncwarp();
         if (lane == 0) {
           bool hasNaN = false;
           for (int a = 0; a < 18; ++a) {
-            double u = ok ? (-sm.B[a] + sm.dvec[a]) : __longlong_as_double(0x7ff8000000000000ll);
+            double u = sm.upd[a];
             if (u != u) { u = 0.0; hasNaN = true; }  // :553-558
             sm.upd[a] = u;
           }
@@ -141,32 +151,38 @@ __global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_const
     // ---- exit: covariance + outputs (StateEstimator.hpp:585-599) -------------------------------------------
     const bool diverged = sm.flags[1] != 0;
     if (!diverged && iters > 0) {
-      // G = (P A + sig2 I)^-1 P ; K H = G A ; K R K^T = sig2 G A G^T
-      form_S(sm, sig2);
-      for (int e = tid; e < 324; e += kThreads) sm.B[e] = sm.P[e];
+      // Joseph form with the LAST iteration's K, H, R (:595-596), all through the 6x6 system:
+      //   K H = U E_c^T,  U = P[:,c] M^-1 A6 ;   K R K^T = sig2 U V^T,  V = P[:,c] M^-1
+      form_M6(sm, sig2, tid, kThreads);
+      if (tid >= 64 && tid < 64 + 72) {  // right-hand sides [A6 | I6]
+        const int e = tid - 64, a = e / 12, c = e % 12;
+        sm.X6[e] = c < 6 ? sm.A6[a * 6 + c] : (a == c - 6 ? 1.0 : 0.0);
+      }
       __syncthreads();
       if (warp == 0) {
-        const bool ok = warp_lu_solve(sm.S, sm.B, 18);
-        if (!ok) for (int e = lane; e < 324; e += 32) sm.B[e] = __longlong_as_double(0x7ff8000000000000ll);
+        const bool ok = warp_lu_solve<6>(sm.M6, sm.X6, 12);
+        if (!ok) for (int e = lane; e < 72; e += 32) sm.X6[e] = __longlong_as_double(0x7ff8000000000000ll);
       }
       __syncthreads();
-      for (int e = tid; e < 324; e += kThreads) {  // W2 = G A18 ; W1 = I - G A18
-        const int a = e / 18, c = e % 18;
-        int cc = -1;
-        if (c < 3) cc = c; else if (c >= 6 && c < 9) cc = c - 3;
-        double s = 0;
-        if (cc >= 0) for (int k = 0; k < 6; ++k) s += sm.B[a * 18 + col6(k)] * sm.A6[k * 6 + cc];
-        sm.W2[e] = s;
-        sm.W1[e] = (a == c ? 1.0 : 0.0) - s;
+      if (tid < 216) {
+        const int which = tid / 108, e = tid % 108, a = e / 6, c = e % 6;
+        double sacc = 0;
+        for (int k = 0; k < 6; ++k) sacc += sm.P[a * 18 + col6(k)] * sm.X6[k * 12 + c + 6 * which];
+        (which ? sm.V : sm.U)[e] = sacc;
       }
       __syncthreads();
-      mat18_mul(sm.S, sm.W1, sm.P, false);  // S = IKH P
-      __syncthreads();
-      for (int e = tid; e < 324; e += kThreads) {  // P <- IKH P IKH^T + sig2 (G A) G^T
+      for (int e = tid; e < 324; e += kThreads) {  // X = (I - K H) P = P - U P[c,:]
         const int i = e / 18, j = e % 18;
-        double s = 0, t = 0;
-        for (int k = 0; k < 18; ++k) { s += sm.S[i * 18 + k] * sm.W1[j * 18 + k]; t += sm.W2[i * 18 + k] * sm.B[j * 18 + k]; }
-        sm.P[e] = s + t * sig2;
+        double sacc = sm.P[e];
+        for (int c = 0; c < 6; ++c) sacc -= sm.U[i * 6 + c] * sm.P[col6(c) * 18 + j];
+        sm.X[e] = sacc;
+      }
+      __syncthreads();
+      for (int e = tid; e < 324; e += kThreads) {  // P <- X (I - K H)^T + sig2 U V^T
+        const int i = e / 18, j = e % 18;
+        double sacc = sm.X[e], t = 0;
+        for (int c = 0; c < 6; ++c) { sacc -= sm.X[i * 18 + col6(c)] * sm.U[j * 6 + c]; t += sm.U[i * 6 + c] * sm.V[j * 6 + c]; }
+        sm.P[e] = sacc + t * sig2;
       }
       __syncthreads();
     }
@@ -335,7 +351,7 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   int n = 0;
   size_t nqs = 0, nqc = 0, nts = 0, ntc = 0;
   int max_q = 0;
-  DevBuf<float4> qs, qc, ts, tc;
+  DevBuf<float4> qs, qc, ts, tc, grid_s, grid_c;
   DevBuf<int> qs_off, qc_off, ts_off, tc_off, ind_s, ind_c, counter;
   DevBuf<double> state_in, cov_in, state_out, cov_out, accum;
   DevBuf<lins_scan_result> results;
@@ -348,7 +364,7 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   PinBuf<lins_scan_result> h_results;
   PinBuf<lins_report> h_reports;
   void release() {
-    qs.release(); qc.release(); ts.release(); tc.release(); qs_off.release(); qc_off.release(); ts_off.release();
+    qs.release(); qc.release(); ts.release(); tc.release(); grid_s.release(); grid_c.release(); qs_off.release(); qc_off.release(); ts_off.release();
     tc_off.release(); ind_s.release(); ind_c.release(); counter.release(); state_in.release(); cov_in.release();
     state_out.release(); cov_out.release(); accum.release(); results.release(); reports.release(); sel_s.release();
     sel_c.release(); coeff_s.release(); coeff_c.release(); mask_s.release(); mask_c.release(); h_pts.release();
@@ -455,6 +471,8 @@ int reserve_outputs(lins_ctx* ctx, Resident& r, bool want_reports, bool want_tra
   CK(r.cov_out.reserve((size_t)r.n * 324));
   CK(r.results.reserve(r.n));
   CK(r.accum.reserve((size_t)r.n * 32));
+  CK(r.grid_s.reserve(r.nts + 4));
+  CK(r.grid_c.reserve(r.ntc + 4));
   CK(r.ind_s.reserve(3 * r.nqs + 4));
   CK(r.ind_c.reserve(2 * r.nqc + 4));
   CK(r.counter.reserve(4));
@@ -476,6 +494,7 @@ BatchView view_of(const Resident& r, bool reports, bool trace) {
   bv.state_in = r.state_in.p; bv.cov_in = r.cov_in.p; bv.state_out = r.state_out.p; bv.cov_out = r.cov_out.p;
   bv.results = r.results.p; bv.reports = reports ? r.reports.p : nullptr;
   bv.ind_s = r.ind_s.p; bv.ind_c = r.ind_c.p;
+  bv.grid_s = r.grid_s.p; bv.grid_c = r.grid_c.p;
   if (trace) {
     bv.sel_s = r.sel_s.p; bv.sel_c = r.sel_c.p; bv.coeff_s = r.coeff_s.p; bv.coeff_c = r.coeff_c.p;
     bv.mask_s = r.mask_s.p; bv.mask_c = r.mask_c.p;
@@ -509,6 +528,8 @@ int stage_single(lins_ctx* ctx, const lins_point* surf_flat, int ns, const lins_
   CK(cudaMemcpyAsync(r.qc_off.p, r.h_off.p + 2, sizeof(int) * 2, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(r.state_in.p, r.h_state.p, sizeof(double) * 20, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(r.cov_in.p, r.h_cov.p, sizeof(double) * 324, cudaMemcpyHostToDevice, ctx->stream));
+  r.nts = (size_t)std::max(std::max(ctx->map_ns, ctx->tree_ns), 0);
+  r.ntc = (size_t)std::max(std::max(ctx->map_nc, ctx->tree_nc), 0);
   int rc = reserve_outputs(ctx, r, true, trace);
   return rc;
 }
@@ -661,6 +682,7 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
   CK(cudaSetDevice(ctx->device));
   Resident& r = ctx->batch;
   const int n = b->n_scans;
+  CK(cudaStreamSynchronize(ctx->stream));  // the pinned staging of a previous upload may still be in flight
   r.n = n;
   if (n == 0) return LINS_OK;
   const int32_t* offs[4] = {b->surf_flat_off, b->corner_sharp_off, b->surf_less_flat_off, b->corner_less_sharp_off};
@@ -682,23 +704,49 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
   CK(r.qs_off.reserve(n + 1)); CK(r.qc_off.reserve(n + 1)); CK(r.ts_off.reserve(n + 1)); CK(r.tc_off.reserve(n + 1));
   CK(r.state_in.reserve((size_t)n * 20)); CK(r.cov_in.reserve((size_t)n * 324));
   // pack 32-B PointXYZI -> 16-B float4 while copying into pinned staging (the copy is needed anyway: user
-  // buffers are pageable), so PCIe moves half the bytes
+  // buffers are pageable), so PCIe moves half the bytes.  The pack is spread over host threads in ~1 M-point
+  // slices; each slice's H2D copy is queued as soon as the slice is packed, so packing and PCIe overlap.
   float4* hp = r.h_pts.p;
   size_t seg[5] = {0, r.nqs, r.nqs + r.nqc, r.nqs + r.nqc + r.nts, total};
-  for (int k = 0; k < 4; ++k) pack_into(hp + seg[k], pts[k], (int)(seg[k + 1] - seg[k]));
+  float4* dsts[4] = {r.qs.p, r.qc.p, r.ts.p, r.tc.p};
+  int* doffs[4] = {r.qs_off.p, r.qc_off.p, r.ts_off.p, r.tc_off.p};
+  {
+    struct Slice { int k; size_t a, b; };
+    std::vector<Slice> slices;
+    const size_t SL = 1u << 18;
+    for (int k = 0; k < 4; ++k)
+      for (size_t a = 0; a < seg[k + 1] - seg[k]; a += SL) slices.push_back(Slice{k, a, std::min(a + SL, seg[k + 1] - seg[k])});
+    std::atomic<size_t> next(0);
+    std::atomic<int> cuda_err(0);
+    const int device = ctx->device;
+    cudaStream_t stream = ctx->stream;
+    auto worker = [&]() {
+      cudaSetDevice(device);
+      for (;;) {
+        size_t i = next.fetch_add(1);
+        if (i >= slices.size()) break;
+        const Slice& sl = slices[i];
+        pack_into(hp + seg[sl.k] + sl.a, pts[sl.k] + sl.a, (int)(sl.b - sl.a));
+        cudaError_t e = cudaMemcpyAsync(dsts[sl.k] + sl.a, hp + seg[sl.k] + sl.a, sizeof(float4) * (sl.b - sl.a), cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) cuda_err.store((int)e);
+      }
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    int nthr = (int)std::min<size_t>(std::min<unsigned>(hw ? hw : 4, 16), std::max<size_t>(slices.size(), 1));
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthr; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    if (cuda_err.load() != 0) return fail(ctx, LINS_E_CUDA, "H2D copy of a packed slice", (cudaError_t)cuda_err.load());
+  }
   for (int k = 0; k < 4; ++k) std::memcpy(r.h_off.p + (size_t)k * (n + 1), offs[k], sizeof(int) * (n + 1));
   for (int i = 0; i < n; ++i) {
     std::memcpy(r.h_state.p + (size_t)i * 20, b->state_in + (size_t)i * 19, sizeof(double) * 19);
     r.h_state.p[(size_t)i * 20 + 19] = 0.0;
   }
   std::memcpy(r.h_cov.p, b->cov_in, sizeof(double) * 324 * (size_t)n);
-  float4* dsts[4] = {r.qs.p, r.qc.p, r.ts.p, r.tc.p};
-  int* doffs[4] = {r.qs_off.p, r.qc_off.p, r.ts_off.p, r.tc_off.p};
-  for (int k = 0; k < 4; ++k) {
-    size_t cnt = seg[k + 1] - seg[k];
-    if (cnt) CK(cudaMemcpyAsync(dsts[k], hp + seg[k], sizeof(float4) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+  for (int k = 0; k < 4; ++k)
     CK(cudaMemcpyAsync(doffs[k], r.h_off.p + (size_t)k * (n + 1), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
-  }
   CK(cudaMemcpyAsync(r.state_in.p, r.h_state.p, sizeof(double) * 20 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(r.cov_in.p, r.h_cov.p, sizeof(double) * 324 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   return reserve_outputs(ctx, r, true, false);

@@ -26,6 +26,12 @@ constexpr int kRingTab = 260;   // ring-start table: first target index with rin
 constexpr int kMaxRing = 256;   // rings outside [0, kMaxRing) or unsorted clouds take the sequential walk
 constexpr int kNAcc = 28;       // 21 (sym 6x6) + 6 (g*r) + 1 (r*r)
 constexpr int kNNChunk = 1024;  // targets per brute-force work item
+// exact 1-NN index: 2-D (x,y) spatial hash, cell edge kCell metres, rebuilt per scan on device
+constexpr int kHashS = 4096;    // buckets, surf targets
+constexpr int kHashC = 1024;    // buckets, corner targets
+constexpr float kCell = 0.5f;
+constexpr float kInvCell = 2.0f;
+constexpr int kGridRounds = 3;  // Chebyshev rings searched before the brute-force fallback
 constexpr unsigned long long kKeyMax = 0xFFFFFFFFFFFFFFFFull;
 
 enum KernelMode { MODE_IESKF = 0, MODE_ASSOC = 1, MODE_ICP_REDUCE = 2, MODE_JACOBIAN = 3 };
@@ -52,6 +58,8 @@ struct BatchView {
   float* coeff_s; float* coeff_c;        // optional (4 per query)
   unsigned char* mask_s; unsigned char* mask_c;  // optional
   double* accum;                         // n x 32 : 28 accumulators + m_surf + m_corner (modes 2,3)
+  float4* grid_s; float4* grid_c;        // scratch: bucket-sorted copies (x,y,z,bits(orig index)) of the 1-NN clouds,
+                                         // same per-scan offsets as the clouds they index
   int* work_counter;
   int qtile;                             // queries staged per pass
 };
@@ -93,10 +101,11 @@ struct Smem {
   int cnt[2];
   double A6[36];
   double y6[6];
-  double S[18 * 18];
-  double B[18 * 18];
-  double W1[18 * 18];
-  double W2[18 * 18];
+  double M6[36];        // A6 P_cc + sig2 I  (6x6 gain system, see form_M6)
+  double X6[6 * 12];    // right-hand sides / solutions of the 6x6 system
+  double U[18 * 6];     // P[:,c] M^-1 A6
+  double V[18 * 6];     // P[:,c] M^-1
+  double X[18 * 18];    // (I - K H) P
   double upd[18];
   double residualNorm;
   int flags[4];         // 0 converged 1 diverged 2 has_nan 3 stop
@@ -104,6 +113,10 @@ struct Smem {
   int sortedS, sortedC;
   int rsS[kRingTab];
   int rsC[kRingTab];
+  int bstartS[kHashS + 1];  // bucket -> first slot in grid_s (exclusive scan of the bucket histogram)
+  int bstartC[kHashC + 1];
+  int scan_tmp[kThreads];
+  int nlist;                // queries whose 1-NN is not yet proven exact
   unsigned long long mbar;
   unsigned int phase;
 };
@@ -170,6 +183,179 @@ __device__ void nn_brute(const float4* sel, unsigned long long* key, int nq, con
     }
     if (valid && bi >= 0) atomicMin(&key[qi], pack_key(best, (unsigned)bi));
   }
+}
+
+
+// ---- exact 1-NN through a 2-D spatial hash ------------------------------------------------------------------
+// cell(p) = (floor(x / kCell), floor(y / kCell)); z is ignored, so a cell is a vertical column.  Any target within
+// (real) distance < r * kCell of the query lies in a cell whose coordinates differ by at most r from the
+// query's, so after all cells of the Chebyshev rings 0..r have been examined the running minimum d is the
+// exact 1-NN as soon as d <= (r * kCell)^2 * (1 - 1e-4)  (the margin dwarfs every f32 rounding involved).
+// Hash collisions only add candidates; every candidate is evaluated with the exact f32 distance expression
+// and packed as (distance bits, original index), so the u64 minimum is "smallest distance, lowest index"
+// regardless of visiting order.  Queries still unproven after kGridRounds rings take the brute-force scan.
+__device__ __forceinline__ int cell_of(float v) {
+  float c = floorf(v * kInvCell);
+  c = fminf(fmaxf(c, -1.0e6f), 1.0e6f);  // monotone clamp; NaN -> -1e6 (such points are never indexed)
+  return (int)c;
+}
+__device__ __forceinline__ unsigned int cell_hash(int ix, int iy) {
+  return ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u);
+}
+
+// Build: histogram -> exclusive scan -> scatter.  src = the cloud the reference's kd-tree was built on.
+template <int H>
+__device__ void grid_build(const float4* __restrict__ src, int T, float4* __restrict__ sorted, int* bstart, int* scan_tmp) {
+  for (int b = threadIdx.x; b <= H; b += kThreads) bstart[b] = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < T; j += kThreads) {
+    const float4 t = __ldg(&src[j]);
+    if (!(isfinite(t.x) && isfinite(t.y) && isfinite(t.z))) continue;  // PCL drops non-finite points
+    atomicAdd(&bstart[cell_hash(cell_of(t.x), cell_of(t.y)) & (H - 1)], 1);
+  }
+  __syncthreads();
+  // exclusive scan of H counters: each thread owns H / kThreads consecutive buckets
+  constexpr int PER = H / kThreads;
+  int loc[PER];
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { loc[k] = bstart[threadIdx.x * PER + k]; sum += loc[k]; }
+  scan_tmp[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {  // 256 partial sums, 8 per lane
+    int part[kThreads / 32];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) { part[k] = scan_tmp[threadIdx.x * (kThreads / 32) + k]; s += part[k]; }
+    int incl = s;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, m); if ((int)threadIdx.x >= m) incl += o; }
+    int run = incl - s;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) { int v = part[k]; scan_tmp[threadIdx.x * (kThreads / 32) + k] = run; run += v; }
+    if (threadIdx.x == 31) bstart[H] = incl;
+  }
+  __syncthreads();
+  {
+    int run = scan_tmp[threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { bstart[threadIdx.x * PER + k] = run; run += loc[k]; }
+  }
+  __syncthreads();
+  // scatter with per-bucket cursors (the counters double as cursors, restored afterwards)
+  for (int j = threadIdx.x; j < T; j += kThreads) {
+    const float4 t = __ldg(&src[j]);
+    if (!(isfinite(t.x) && isfinite(t.y) && isfinite(t.z))) continue;
+    const int pos = atomicAdd(&bstart[cell_hash(cell_of(t.x), cell_of(t.y)) & (H - 1)], 1);
+    sorted[pos] = make_float4(t.x, t.y, t.z, __int_as_float(j));
+  }
+  __syncthreads();
+  // cursors now hold the END of each bucket == start of the next: shift back
+  {
+    int prev[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      const int b = threadIdx.x * PER + k;
+      prev[k] = b == 0 ? 0 : bstart[b - 1];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) bstart[threadIdx.x * PER + k] = prev[k];
+  }
+  __syncthreads();
+}
+
+// (dx,dy) of the k-th cell of Chebyshev ring r (r >= 1: 8r cells; r == 0: the centre)
+__device__ __forceinline__ void ring_cell(int r, int k, int& dx, int& dy) {
+  if (r == 0) { dx = 0; dy = 0; return; }
+  const int side = k / (2 * r), pos = k - side * 2 * r;
+  if (side == 0) { dx = -r + pos; dy = -r; }
+  else if (side == 1) { dx = r; dy = -r + pos; }
+  else if (side == 2) { dx = r - pos; dy = r; }
+  else { dx = -r; dy = r - pos; }
+}
+
+// brute-force scan of ALL targets for the listed queries: one warp per query, coalesced 16-B loads
+__device__ void nn_brute_listed(const float4* sel, unsigned long long* key, const int* list, int nlist,
+                                const float4* __restrict__ tgt, int T) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int li = warp; li < nlist; li += kWarps) {
+    const int qi = list[li];
+    const float4 s = sel[qi];
+    unsigned long long best = kKeyMax;
+    for (int j = lane; j < T; j += 32) {
+      const float4 t = __ldg(&tgt[j]);
+      const float d = sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z);
+      if (d < __int_as_float(0x7f800000)) { const unsigned long long k = pack_key(d, (unsigned)j); best = k < best ? k : best; }
+    }
+    best = warp_min_u64(best);
+    if (lane == 0) key[qi] = best;  // the full scan supersedes whatever the grid rounds found
+  }
+}
+
+template <int H>
+__device__ void nn_grid(Smem& sm, const float4* sel, unsigned long long* key, int nq, const float4* sorted,
+                        const int* bstart, const float4* __restrict__ tgt, int T, int* list) {
+  // round 0+1: centre cell + ring 1 (9 cells) for every query
+  for (int item = threadIdx.x; item < nq * 9; item += kThreads) {
+    const int qi = item / 9, k = item - qi * 9;
+    const float4 s = sel[qi];
+    const int cx = cell_of(s.x) + (k % 3) - 1, cy = cell_of(s.y) + (k / 3) - 1;
+    const unsigned b = cell_hash(cx, cy) & (H - 1);
+    unsigned long long best = kKeyMax;
+    for (int p = bstart[b], e = bstart[b + 1]; p < e; ++p) {
+      const float4 t = sorted[p];
+      const float d = sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z);
+      if (d < __int_as_float(0x7f800000)) { const unsigned long long kk = pack_key(d, (unsigned)__float_as_int(t.w)); best = kk < best ? kk : best; }
+    }
+    if (best != kKeyMax) atomicMin(&key[qi], best);
+  }
+  if (threadIdx.x == 0) sm.nlist = 0;
+  __syncthreads();
+  // classify: proven iff d <= (1 * kCell)^2 * (1 - 1e-4)
+  {
+    const float thr = kCell * kCell * 0.9999f;
+    for (int qi = threadIdx.x; qi < nq; qi += kThreads) {
+      const unsigned long long k1 = key[qi];
+      const float d = __uint_as_float((unsigned)(k1 >> 32));
+      if (!(k1 != kKeyMax && d <= thr)) list[atomicAdd(&sm.nlist, 1)] = qi;
+    }
+  }
+  __syncthreads();
+  for (int r = 2; r <= kGridRounds && sm.nlist > 0; ++r) {
+    const int nl = sm.nlist, ncell = 8 * r;
+    for (int item = threadIdx.x; item < nl * ncell; item += kThreads) {
+      const int li = item / ncell, k = item - li * ncell;
+      const int qi = list[li];
+      const float4 s = sel[qi];
+      int dx, dy;
+      ring_cell(r, k, dx, dy);
+      const unsigned b = cell_hash(cell_of(s.x) + dx, cell_of(s.y) + dy) & (H - 1);
+      unsigned long long best = kKeyMax;
+      for (int p = bstart[b], e = bstart[b + 1]; p < e; ++p) {
+        const float4 t = sorted[p];
+        const float d = sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z);
+        if (d < __int_as_float(0x7f800000)) { const unsigned long long kk = pack_key(d, (unsigned)__float_as_int(t.w)); best = kk < best ? kk : best; }
+      }
+      if (best != kKeyMax) atomicMin(&key[qi], best);
+    }
+    __syncthreads();
+    // compact the list in place (order irrelevant): one thread does it serially (lists are short)
+    if (threadIdx.x == 0) {
+      const float thr = (r * kCell) * (r * kCell) * 0.9999f;
+      int w = 0;
+      for (int li = 0; li < nl; ++li) {
+        const int qi = list[li];
+        const unsigned long long k1 = key[qi];
+        const float d = __uint_as_float((unsigned)(k1 >> 32));
+        if (!(k1 != kKeyMax && d <= thr)) list[w++] = qi;
+      }
+      sm.nlist = w;
+    }
+    __syncthreads();
+  }
+  if (sm.nlist > 0) nn_brute_listed(sel, key, list, sm.nlist, tgt, T);
+  __syncthreads();
 }
 
 // walk keys: high 32 = f32 distance bits, low 32 = visiting order (forward walk ascending j first, then the
@@ -376,18 +562,19 @@ __device__ void block_reduce_acc(Smem& sm, double* acc, int cs, int cc) {
   __syncthreads();
 }
 
-// 18x18 LU with partial pivoting by one warp; S row-major (destroyed), B = 18 x nrhs row-major (-> solution).
-// Pivot choice = first maximum of |column| from the diagonal down (same as a sequential scan).
+// N x N (N <= 32) LU with partial pivoting by one warp; S row-major (destroyed), B = N x nrhs row-major
+// (-> solution).  Pivot choice = first maximum of |column| from the diagonal down (same as a sequential scan).
+template <int N>
 __device__ bool warp_lu_solve(double* S, double* B, int nrhs) {
   const int lane = threadIdx.x & 31;
   bool ok = true;
-  for (int k = 0; k < 18; ++k) {
+  for (int k = 0; k < N; ++k) {
     double v = -1.0;
-    if (lane >= k && lane < 18) {
-      v = fabs(S[lane * 18 + k]);
+    if (lane >= k && lane < N) {
+      v = fabs(S[lane * N + k]);
       if (v != v) v = (lane == k) ? __longlong_as_double(0x7ff8000000000000ll) : -1.0;
     }
-    // NaN on the diagonal poisons the step (sequential scan keeps best = NaN)
+    // NaN on the diagonal poisons the step (a sequential scan would keep best = NaN)
     unsigned nanmask = __ballot_sync(0xffffffffu, v != v);
     int piv = lane;
 #pragma unroll
@@ -398,26 +585,26 @@ __device__ bool warp_lu_solve(double* S, double* B, int nrhs) {
     }
     if (nanmask != 0u || !(v > 0.0)) { ok = false; break; }
     if (piv != k) {
-      if (lane < 18) { double t = S[k * 18 + lane]; S[k * 18 + lane] = S[piv * 18 + lane]; S[piv * 18 + lane] = t; }
+      if (lane < N) { double t = S[k * N + lane]; S[k * N + lane] = S[piv * N + lane]; S[piv * N + lane] = t; }
       for (int j = lane; j < nrhs; j += 32) { double t = B[k * nrhs + j]; B[k * nrhs + j] = B[piv * nrhs + j]; B[piv * nrhs + j] = t; }
     }
     __syncwarp();
-    const double inv = 1.0 / S[k * 18 + k];
-    if (lane > k && lane < 18) {
-      const double f = S[lane * 18 + k] * inv;
+    const double inv = 1.0 / S[k * N + k];
+    if (lane > k && lane < N) {
+      const double f = S[lane * N + k] * inv;
       if (f != 0.0) {
-        for (int j = k + 1; j < 18; ++j) S[lane * 18 + j] -= f * S[k * 18 + j];
+        for (int j = k + 1; j < N; ++j) S[lane * N + j] -= f * S[k * N + j];
         for (int j = 0; j < nrhs; ++j) B[lane * nrhs + j] -= f * B[k * nrhs + j];
       }
     }
     __syncwarp();
   }
   if (!ok) return false;
-  for (int k = 17; k >= 0; --k) {
-    const double inv = 1.0 / S[k * 18 + k];
+  for (int k = N - 1; k >= 0; --k) {
+    const double inv = 1.0 / S[k * N + k];
     for (int j = lane; j < nrhs; j += 32) {
       double s = B[k * nrhs + j];
-      for (int c = k + 1; c < 18; ++c) s -= S[k * 18 + c] * B[c * nrhs + j];
+      for (int c = k + 1; c < N; ++c) s -= S[k * N + c] * B[c * nrhs + j];
       B[k * nrhs + j] = s * inv;
     }
     __syncwarp();
@@ -462,16 +649,17 @@ __device__ void build_A6(Smem& sm) {
   }
 }
 
-// S = P A + sig2 I (18x18), using all threads
-__device__ void form_S(Smem& sm, double sig2) {
-  for (int e = threadIdx.x; e < 324; e += kThreads) {
-    const int a = e / 18, c = e % 18;
+// M = A6 P_cc + sig2 I6: the 6x6 system of the gain in push-through form.  With H = H6 E_c^T (only the 6
+// structural columns c = {0,1,2,6,7,8} are non-zero) and R = sig2 I:
+//   K = P H^T (H P H^T + R)^-1 = P[:,c] (A6 P[c,c] + sig2 I6)^-1 H6^T,   A6 = H6^T H6
+// so  K (r + H d) = P[:,c] M^-1 (b6 + A6 d_c)  and nothing larger than 6x6 is ever factorised.
+__device__ void form_M6(Smem& sm, double sig2, int idx, int stride) {
+  for (int t = idx; t < 36; t += stride) {
+    const int a = t / 6, c = t % 6;
     double s = 0;
-    int cc = -1;
-    if (c < 3) cc = c; else if (c >= 6 && c < 9) cc = c - 3;
-    if (cc >= 0) for (int k = 0; k < 6; ++k) s += sm.P[a * 18 + col6(k)] * sm.A6[k * 6 + cc];
+    for (int k = 0; k < 6; ++k) s += sm.A6[a * 6 + k] * sm.P[col6(k) * 18 + col6(c)];
     if (a == c) s += sig2;
-    sm.S[e] = s;
+    sm.M6[t] = s;
   }
 }
 
@@ -502,17 +690,6 @@ __device__ void box_plus(Smem& sm) {
   l[6] = r.x; l[7] = r.y; l[8] = r.z; l[9] = r.w;
 }
 
-// C = A * B (18x18, row-major), optionally B transposed; all threads
-__device__ void mat18_mul(double* C, const double* A, const double* B, bool transB) {
-  for (int e = threadIdx.x; e < 324; e += kThreads) {
-    const int i = e / 18, j = e % 18;
-    double s = 0;
-    if (transB) for (int k = 0; k < 18; ++k) s += A[i * 18 + k] * B[j * 18 + k];
-    else for (int k = 0; k < 18; ++k) s += A[i * 18 + k] * B[k * 18 + j];
-    C[e] = s;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // One association + reduction pass over all queries of the scan at the current linearisation point.
 // Fills sm.acc (28 sums) and sm.cnt (accepted surf / corner counts).
@@ -529,6 +706,8 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
   const float4* __restrict__ nnC = bv.nn_c ? bv.nn_c + bv.nn_c_off[scan] : tgtC;
   const int TnS = bv.nn_s ? bv.nn_s_off[scan + 1] - bv.nn_s_off[scan] : Ts;
   const int TnC = bv.nn_c ? bv.nn_c_off[scan + 1] - bv.nn_c_off[scan] : Tc;
+  const float4* gridS = bv.grid_s + (bv.nn_s ? bv.nn_s_off[scan] : ts0);
+  const float4* gridC = bv.grid_c + (bv.nn_c ? bv.nn_c_off[scan] : tc0);
   const bool search = (iter % kp.icp_freq) == 0;
   const bool weighted = iter >= kp.icp_freq;
   const float nearf = (float)kp.nearest_sq;
@@ -569,8 +748,8 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
     __syncthreads();
     if (search) {
       // ---- A3/A4: exact 1-NN ------------------------------------------------------------------------------
-      if (nsT > 0 && TnS > 0) nn_brute(selbuf, key, nsT, nnS, TnS);
-      if (nq - nsT > 0 && TnC > 0) nn_brute(selbuf + nsT, key + nsT, nq - nsT, nnC, TnC);
+      if (nsT > 0 && TnS > 0) nn_grid<kHashS>(sm, selbuf, key, nsT, gridS, sm.bstartS, nnS, TnS, indbuf);
+      if (nq - nsT > 0 && TnC > 0) nn_grid<kHashC>(sm, selbuf + nsT, key + nsT, nq - nsT, gridC, sm.bstartC, nnC, TnC, indbuf);
       __syncthreads();
       // ---- ring walks ---------------------------------------------------------------------------------------
       const int fwdS = min(ns, Ts), fwdC = min(nc, Tc);  // :859 / :983 loop-bound quirk (+ OOB clamp)

@@ -143,6 +143,28 @@ def test_unsorted_rings_take_the_sequential_walk(gpu, ob, golden_batch, defs):
     _check_assoc(gpu.associate(u["surf_flat"], u["corner_sharp"], u["state"], 1), o.associate(u["surf_flat"], u["corner_sharp"], u["state"], 1))
 
 
+def test_far_and_unmatched_queries(gpu, ob, golden_batch):
+    """The device 1-NN index must stay exact when the nearest target is far away: queries displaced by 0.6 m,
+    1.3 m, 3 m (outer search rings / brute-force fallback) and 40 m (no target within the 5 m gate)."""
+    prm = ob.LinsParams.shipped()
+    gpu.set_params(prm)
+    u = golden_batch.unit(2)
+    o = ob.Oracle(prm, use_kdtree=False)
+    o.set_map(u["surf_less_flat"], u["corner_less_sharp"])
+    gpu.set_map(u["surf_less_flat"], u["corner_less_sharp"])
+    for shift in (0.6, 1.3, 3.0, 40.0):
+        st = u["state"].copy()
+        st[0] += shift * 10.0  # s = 10 * frac(intensity) in [0, 1): displaces each query by up to `shift` * 10 * 0.1
+        st[2] += 0.3 * shift
+        go, oo = gpu.associate(u["surf_flat"], u["corner_sharp"], st, 0), o.associate(u["surf_flat"], u["corner_sharp"], st, 0)
+        _check_assoc(go, oo, f"shift {shift}")
+    nan_state = u["state"].copy()
+    nan_state[0] = np.nan
+    go, oo = gpu.associate(u["surf_flat"], u["corner_sharp"], nan_state, 0), o.associate(u["surf_flat"], u["corner_sharp"], nan_state, 0)
+    assert np.array_equal(go["surf_ind"], oo["surf_ind"]) and np.array_equal(go["corner_ind"], oo["corner_ind"])
+    assert not go["surf_mask"].any() and not oo["surf_mask"].any()
+
+
 def test_icp_freq_reuses_indices(gpu, ob, golden_batch):
     """ICP_FREQ = 2: odd iterations reuse pointSearch*Ind of the previous one (StateEstimator.hpp:844, :970) and
     the robust weight starts at iter >= ICP_FREQ."""
