@@ -18,7 +18,7 @@ from .ctypes_defs import (Batch, COV_SIZE, LinsBatchDesc, LinsParams, LinsReport
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "liblins_gpu.so")
+LIB_PATH = os.environ.get("LINS_GPU_LIB") or os.path.join(_PKG, "liblins_gpu.so")  # override only for A/B experiments
 CUDA_DIR = os.path.join(_PKG, "csrc", "cuda")
 
 # every symbol include/lins_gpu.h declares
@@ -27,6 +27,7 @@ EXPORTS = [
     "lins_gpu_set_map", "lins_gpu_ieskf", "lins_gpu_associate", "lins_gpu_estimate_transform", "lins_gpu_update_map",
     "lins_gpu_batch_upload", "lins_gpu_batch_run", "lins_gpu_batch_download", "lins_gpu_ieskf_batch",
     "lins_gpu_batch_results_device", "lins_gpu_batch_jacobian_pass", "lins_gpu_launch_count", "lins_gpu_sync",
+    "lins_gpu_debug_phase_cycles",
 ]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
@@ -74,6 +75,7 @@ def lib():
         L.lins_gpu_launch_count.argtypes = [vp]
         L.lins_gpu_launch_count.restype = C.c_int64
         L.lins_gpu_sync.argtypes = [vp]
+        L.lins_gpu_debug_phase_cycles.argtypes = [vp, C.c_int, vp]
         _LIB = L
     return _LIB
 
@@ -120,6 +122,11 @@ class LinsGpu:
 
     def sync(self):
         self._ck(self.L.lins_gpu_sync(self.h))
+
+    def phase_cycles(self, enable=True, read=False):
+        out = np.zeros(32, np.int64) if read else None
+        self._ck(self.L.lins_gpu_debug_phase_cycles(self.h, int(enable), ptr(out)))
+        return out
 
     # ---- single-scan seam ---------------------------------------------------------------------------------
     def set_map(self, surf_less_flat, corner_less_sharp):

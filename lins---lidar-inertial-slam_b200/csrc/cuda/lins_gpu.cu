@@ -31,7 +31,7 @@ __host__ __device__ inline size_t smem_bytes_for(int qtile) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_constant__ BatchView bv,
+__global__ void __launch_bounds__(kThreads, 2) lins_ieskf_kernel(const __grid_constant__ BatchView bv,
                                                               const __grid_constant__ KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int Q = bv.qtile;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_const
   __syncthreads();
 
   for (;;) {
-    if (tid == 0) sm.scan = atomicAdd(bv.work_counter, 1);
+    if (tid == 0) { sm.scan = atomicAdd(bv.work_counter, 1); sm.tlast = clock64(); }
     __syncthreads();
     const int scan = sm.scan;
     if (scan >= bv.n_scans) break;
@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_const
     }
     lins_report* rep = bv.reports ? bv.reports + scan : nullptr;
     int iters = 0;
+    LINS_TICK(0);
 
     if (MODE == MODE_ASSOC || MODE == MODE_ICP_REDUCE) {
       if (tid == 0) compute_iter_consts(sm);
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_const
     for (int iter = 0; iter < kp.num_iter; ++iter) {
       if (tid == 0) compute_iter_consts(sm);
       __syncthreads();
+      LINS_TICK(1);
       association_pass<MODE>(sm, bv, kp, scan, iter, qpt, selbuf, key, indbuf);
       build_A6(sm);
       if (tid == 128) box_minus(sm);
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_const
         }
       }
       __syncthreads();
+      LINS_TICK(8);
       iters = iter + 1;
       if (sm.flags[3]) break;
     }
@@ -207,6 +210,7 @@ __global__ void __launch_bounds__(kThreads) lins_ieskf_kernel(const __grid_const
       if (rep) { rep->iters = iters; rep->converged = sm.flags[0]; rep->diverged = sm.flags[1]; rep->has_nan = sm.flags[2]; }
     }
     __syncthreads();
+    LINS_TICK(9);
   }
 }
 
@@ -353,6 +357,7 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   int max_q = 0;
   DevBuf<float4> qs, qc, ts, tc, grid_s, grid_c;
   DevBuf<int> qs_off, qc_off, ts_off, tc_off, ind_s, ind_c, counter;
+  DevBuf<long long> timers;
   DevBuf<double> state_in, cov_in, state_out, cov_out, accum;
   DevBuf<lins_scan_result> results;
   DevBuf<lins_report> reports;
@@ -391,6 +396,7 @@ struct lins_ctx {
   DevBuf<int> map_off;  // 4 x 2 ints: [0,ns][0,nc][0,tns][0,tnc]
   int map_ns = -1, map_nc = -1, tree_ns = -1, tree_nc = -1;
   bool tree_is_map = true;
+  bool timers_on = false;
   DevBuf<float4> tmp_pts;
   DevBuf<double> tmp_lin;
   PinBuf<float4> h_tmp;
@@ -758,6 +764,11 @@ int lins_gpu_batch_run(lins_ctx* ctx) {
   if (r.n <= 0) return fail(ctx, LINS_E_INVALID, "no resident batch");
   CK(cudaSetDevice(ctx->device));
   BatchView bv = view_of(r, true, false);
+  if (ctx->timers_on) {
+    CK(r.timers.reserve(32));
+    CK(cudaMemsetAsync(r.timers.p, 0, sizeof(long long) * 32, ctx->stream));
+    bv.timers = r.timers.p;
+  }
   return launch(ctx, bv, make_kparams(ctx->prm, MODE_IESKF, 0));
 }
 
@@ -794,6 +805,20 @@ int lins_gpu_batch_results_device(lins_ctx* ctx, void** dev_ptr, int* n_scans) {
   if (!ctx || !dev_ptr) return LINS_E_INVALID;
   *dev_ptr = ctx->batch.results.p;
   if (n_scans) *n_scans = ctx->batch.n;
+  return LINS_OK;
+}
+
+// Diagnostics: enable per-phase cycle counters for lins_gpu_batch_run (enable != 0), and/or read the 32
+// counters of the last run (out may be NULL).  Slot meaning: see LINS_TICK sites in lins_gpu.cu / lins_kernels.cuh.
+int lins_gpu_debug_phase_cycles(lins_ctx* ctx, int enable, long long* out) {
+  if (!ctx) return LINS_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  if (out) {
+    if (!ctx->batch.timers.p) return fail(ctx, LINS_E_INVALID, "timers were not enabled for the last run");
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, ctx->batch.timers.p, sizeof(long long) * 32, cudaMemcpyDeviceToHost));
+  }
+  ctx->timers_on = enable != 0;
   return LINS_OK;
 }
 

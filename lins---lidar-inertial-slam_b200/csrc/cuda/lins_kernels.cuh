@@ -61,6 +61,7 @@ struct BatchView {
   float4* grid_s; float4* grid_c;        // scratch: bucket-sorted copies (x,y,z,bits(orig index)) of the 1-NN clouds,
                                          // same per-scan offsets as the clouds they index
   int* work_counter;
+  long long* timers;                     // optional: per-phase SM cycles summed over CTAs (diagnostics), 32 slots
   int qtile;                             // queries staged per pass
 };
 
@@ -119,7 +120,18 @@ struct Smem {
   int nlist;                // queries whose 1-NN is not yet proven exact
   unsigned long long mbar;
   unsigned int phase;
+  long long tlast;
 };
+
+// phase timers (thread 0 of each CTA; compiled in, enabled when bv.timers != nullptr)
+#define LINS_TICK(k)                                                                   \
+  do {                                                                                 \
+    if (bv.timers && threadIdx.x == 0) {                                               \
+      const long long _t = clock64();                                                  \
+      atomicAdd((unsigned long long*)&bv.timers[k], (unsigned long long)(_t - sm.tlast)); \
+      sm.tlast = _t;                                                                   \
+    }                                                                                  \
+  } while (0)
 
 // ---------------------------------------------------------------------------------------------------------
 // per-iteration constants (thread 0)
@@ -740,17 +752,20 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
       __syncthreads();
       if (threadIdx.x == 0) sm.phase = ph + 1u;
     }
+    LINS_TICK(2);
     // ---- A2: de-skew -------------------------------------------------------------------------------------
     for (int i = threadIdx.x; i < nq; i += kThreads) {
       selbuf[i] = transform_to_start(qpt[i], sm, kp.scan_period);
       key[i] = kKeyMax;
     }
     __syncthreads();
+    LINS_TICK(3);
     if (search) {
       // ---- A3/A4: exact 1-NN ------------------------------------------------------------------------------
       if (nsT > 0 && TnS > 0) nn_grid<kHashS>(sm, selbuf, key, nsT, gridS, sm.bstartS, nnS, TnS, indbuf);
       if (nq - nsT > 0 && TnC > 0) nn_grid<kHashC>(sm, selbuf + nsT, key + nsT, nq - nsT, gridC, sm.bstartC, nnC, TnC, indbuf);
       __syncthreads();
+      LINS_TICK(4);
       // ---- ring walks ---------------------------------------------------------------------------------------
       const int fwdS = min(ns, Ts), fwdC = min(nc, Tc);  // :859 / :983 loop-bound quirk (+ OOB clamp)
       for (int i = warp; i < nq; i += kWarps) {
@@ -787,6 +802,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
       }
     }
     __syncthreads();
+    LINS_TICK(5);
     // ---- A5/A6 residuals + A7-A9 fold ----------------------------------------------------------------------
     for (int i = threadIdx.x; i < nq; i += kThreads) {
       const bool surf = i < nsT;
@@ -821,7 +837,9 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
       }
     }
   }
+  LINS_TICK(6);
   block_reduce_acc(sm, acc, cntS, cntC);
+  LINS_TICK(7);
 }
 
 }  // namespace lins_dev

@@ -1,0 +1,22 @@
+"""Per-phase cycle breakdown of the fused kernel (diagnostics; run on a GPU box)."""
+import importlib, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+capi = importlib.import_module("lins---lidar-inertial-slam_b200.capi")
+synth = importlib.import_module("lins---lidar-inertial-slam_b200.synth")
+defs = importlib.import_module("lins---lidar-inertial-slam_b200.ctypes_defs")
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+b = synth.generate("config3", n=n, seed0=1000)
+g = capi.LinsGpu(defs.LinsParams.shipped())
+g.batch_upload(b); g.batch_run(); g.sync()
+g.phase_cycles(enable=True)
+g.batch_run(); g.sync()
+t = g.phase_cycles(enable=False, read=True)
+_, _, res, _ = g.batch_download(states=False, covs=False)
+its = int(res["iters"].sum())
+names = ["setup(prior,ring tables,index build)", "iter consts", "tile stage (TMA)", "de-skew", "1-NN grid", "ring walks", "residual+fold", "block reduce", "solve+update", "exit cov+outputs"]
+tot = t[:10].sum()
+print(f"scans {n} iterations {its}  total CTA-cycles {tot:.3e}  per iteration {tot/its:.0f} cycles")
+for k, nm in enumerate(names):
+    per = t[k] / (n if k in (0, 9) else its)
+    print(f"  {nm:40s} {100*t[k]/tot:5.1f}%   {per:9.0f} cycles per {'scan' if k in (0,9) else 'iteration'}")
