@@ -1,0 +1,224 @@
+// One association + reduction pass over all queries of a scan at the current linearisation point
+// (rows A2-A9 of SURVEY.md §8; reference findCorrespondingSurfFeatures / findCorrespondingCornerFeatures,
+// lins/include/StateEstimator.hpp:829-1063, + the measurement assembly :499-532 folded into 28 sums).
+//
+// Fast path (sm.az_ok): targets are ring-sorted, the (ring, azimuth) index of lins_assoc_az.cuh is valid.
+// Legacy path: any ring order / ring values / a 1-NN cloud that differs from the walk cloud (the stale-index
+// quirk of :1156-1160): brute-force exact 1-NN + the plain (or literal sequential) walks over global memory.
+#pragma once
+#include "lins_assoc_az.cuh"
+
+namespace lins_dev {
+
+struct PassBuffers {
+  float4* qpt;               // staged queries (x, y, z, intensity) of the current tile
+  float4* sel;               // de-skewed queries (pointSel)
+  unsigned long long* key;   // legacy path: 1-NN keys
+  int* pos;                  // 3 per query.  fast path: slots in the sorted copies (closest, Ind2, Ind3);
+                             //               legacy path: original indices
+  float4* qa;                // fast path: (azimuth, rho, -, -) of the de-skewed query
+  int4* qw;                  // fast path: search windows w1 / w2 / w3 and (ring << 24 | index) of the closest point
+  const float4* azS;         // sorted copies (shared or global)
+  const float4* azC;
+};
+
+template <int MODE>
+__device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& kp, int scan, int iter, const PassBuffers& pb,
+                                 bool first_pass_of_scan) {
+  const int qs0 = bv.qs_off[scan], ns = bv.qs_off[scan + 1] - qs0;
+  const int qc0 = bv.qc_off[scan], nc = bv.qc_off[scan + 1] - qc0;
+  const int ts0 = bv.ts_off[scan], Ts = bv.ts_off[scan + 1] - ts0;
+  const int tc0 = bv.tc_off[scan], Tc = bv.tc_off[scan + 1] - tc0;
+  const float4* __restrict__ tgtS = bv.ts + ts0;
+  const float4* __restrict__ tgtC = bv.tc + tc0;
+  const float4* __restrict__ nnS = bv.nn_s ? bv.nn_s + bv.nn_s_off[scan] : tgtS;
+  const float4* __restrict__ nnC = bv.nn_c ? bv.nn_c + bv.nn_c_off[scan] : tgtC;
+  const int TnS = bv.nn_s ? bv.nn_s_off[scan + 1] - bv.nn_s_off[scan] : Ts;
+  const int TnC = bv.nn_c ? bv.nn_c_off[scan + 1] - bv.nn_c_off[scan] : Tc;
+  const bool search = (iter % kp.icp_freq) == 0;
+  const bool weighted = iter >= kp.icp_freq;
+  const float nearf = (float)kp.nearest_sq;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool fast = sm.az_ok != 0;
+  const int fwdS = min(ns, Ts), fwdC = min(nc, Tc);  // :859 / :983 loop-bound quirk (+ OOB clamp)
+  const int ntot = ns + nc;
+  // previous answers are usable as bounds only if this scan has a single query tile (slots stay in shared memory)
+  const bool seeded = fast && !first_pass_of_scan && ntot <= bv.qtile;
+
+  AzIndex ixS, ixC;
+  ixS.pts = pb.azS; ixS.bstart = sm.azTabS; ixS.nb = sm.nbS; ixS.nrings = sm.nringsS; ixS.T = Ts;
+  ixC.pts = pb.azC; ixC.bstart = sm.azTabC; ixC.nb = sm.nbC; ixC.nrings = sm.nringsC; ixC.T = Tc;
+
+  double acc[kNAcc];
+#pragma unroll
+  for (int k = 0; k < kNAcc; ++k) acc[k] = 0.0;
+  int cntS = 0, cntC = 0;
+
+  for (int q0 = 0; q0 < ntot; q0 += bv.qtile) {
+    const int nq = min(bv.qtile, ntot - q0);
+    const int nsT = max(0, min(ns - q0, nq));  // sub-lists of this tile: surf [0, nsT) then corner [nsT, nq)
+    // ---- stage the tile's queries (1-D TMA) --------------------------------------------------------------------
+    __syncthreads();  // previous tile fully consumed
+    if (ntot > bv.qtile || first_pass_of_scan) {  // a single-tile scan keeps its queries staged across iterations
+      if (threadIdx.x == 0) {
+        uint32_t bytes = 0;
+        if (nsT > 0) bytes += (uint32_t)nsT * 16u;
+        if (nq - nsT > 0) bytes += (uint32_t)(nq - nsT) * 16u;
+        fence_proxy_async();
+        mbar_expect_tx(&sm.mbar, bytes);
+        if (nsT > 0) tma_load_1d(pb.qpt, bv.qs + qs0 + q0, (uint32_t)nsT * 16u, &sm.mbar);
+        if (nq - nsT > 0) tma_load_1d(pb.qpt + nsT, bv.qc + qc0 + max(0, q0 - ns), (uint32_t)(nq - nsT) * 16u, &sm.mbar);
+      }
+      const unsigned int ph = sm.phase;  // one mbarrier phase per staged tile
+      mbar_wait(&sm.mbar, ph & 1u);
+      __syncthreads();
+      if (threadIdx.x == 0) sm.phase = ph + 1u;
+    }
+    LINS_TICK(2);
+    // ---- A2: de-skew ---------------------------------------------------------------------------------------------
+    for (int i = threadIdx.x; i < nq; i += kThreads) {
+      pb.sel[i] = transform_to_start(pb.qpt[i], sm, kp.scan_period);
+      pb.key[i] = kKeyMax;
+    }
+    __syncthreads();
+    LINS_TICK(3);
+    if (search && fast) {
+      // ---- A3/A4 fast path, four short phases.  Scalar preparation (atan2f, asinf, bounds) runs one THREAD per
+      // query so that all queries proceed in parallel; the memory scans run one WARP per query.
+      for (int i = threadIdx.x; i < nq; i += kThreads) {  // P1
+        float4 qa;
+        const bool surf = i < nsT;
+        const int w1 = az_prepare_nn(surf ? ixS : ixC, pb.sel[i], nearf, seeded ? pb.pos[3 * i] : -1, qa);
+        pb.qa[i] = qa;
+        pb.qw[i] = make_int4(w1, 0, 0, 0);
+      }
+      __syncthreads();
+      for (int i = warp; i < nq; i += kWarps) {  // P2
+        const int w1 = pb.qw[i].x;
+        unsigned long long k1 = kKeyMax;
+        int p1 = -1;
+        if (w1 >= 0) k1 = az_scan_nn(i < nsT ? ixS : ixC, pb.sel[i], w1, p1);
+        if (lane == 0) { pb.key[i] = k1; pb.pos[3 * i] = p1; }
+      }
+      __syncthreads();
+      LINS_TICK(4);
+      for (int i = threadIdx.x; i < nq; i += kThreads) {  // P3
+        const bool surf = i < nsT;
+        const int gq = q0 + i;
+        int w2 = 0, w3 = 0, ccr = 0;
+        const int sd2 = seeded ? pb.pos[3 * i + 1] : -1, sd3 = seeded ? pb.pos[3 * i + 2] : -1;
+        bool found;
+        if (surf) found = az_prepare_walk<true>(ixS, pb.sel[i], pb.qa[i], pb.key[i], pb.pos[3 * i], sd2, sd3, fwdS, nearf, kp.nearest_sq, w2, w3, ccr);
+        else found = az_prepare_walk<false>(ixC, pb.sel[i], pb.qa[i], pb.key[i], pb.pos[3 * i], sd2, sd3, fwdC, nearf, kp.nearest_sq, w2, w3, ccr);
+        pb.qw[i] = make_int4(found ? 1 : -1, w2, w3, ccr);
+        if (!found) {
+          pb.pos[3 * i] = -1; pb.pos[3 * i + 1] = -1; pb.pos[3 * i + 2] = -1;
+          if (surf) { int* o = bv.ind_s + 3 * (size_t)(qs0 + gq); o[0] = -1; o[1] = -1; o[2] = -1; }
+          else { int* o = bv.ind_c + 2 * (size_t)(qc0 + gq - ns); o[0] = -1; o[1] = -1; }
+        }
+      }
+      __syncthreads();
+      for (int i = warp; i < nq; i += kWarps) {  // P4
+        const int4 w = pb.qw[i];
+        if (w.x < 0) continue;
+        const bool surf = i < nsT;
+        const int gq = q0 + i;
+        int i2, i3, p2, p3;
+        if (surf) az_scan_walk<true>(ixS, pb.sel[i], w.w, w.y, w.z, fwdS, nearf, i2, i3, p2, p3);
+        else az_scan_walk<false>(ixC, pb.sel[i], w.w, w.y, w.z, fwdC, nearf, i2, i3, p2, p3);
+        if (lane == 0) {
+          pb.pos[3 * i + 1] = p2; pb.pos[3 * i + 2] = p3;
+          const int i1 = w.w & 0x00ffffff;
+          if (surf) { int* o = bv.ind_s + 3 * (size_t)(qs0 + gq); o[0] = i1; o[1] = i2; o[2] = i3; }
+          else { int* o = bv.ind_c + 2 * (size_t)(qc0 + gq - ns); o[0] = i1; o[1] = i2; }
+        }
+      }
+    } else if (search) {
+      // ---- legacy: brute-force exact 1-NN ----------------------------------------------------------------------------
+      if (nsT > 0 && TnS > 0) nn_brute(pb.sel, pb.key, nsT, nnS, TnS);
+      if (nq - nsT > 0 && TnC > 0) nn_brute(pb.sel + nsT, pb.key + nsT, nq - nsT, nnC, TnC);
+      __syncthreads();
+      LINS_TICK(4);
+      for (int i = warp; i < nq; i += kWarps) {
+        const bool surf = i < nsT;
+        const unsigned long long k1 = pb.key[i];
+        const float d1 = __uint_as_float((unsigned)(k1 >> 32));
+        const int c = (int)(unsigned)(k1 & 0xffffffffu);
+        const bool found = (k1 != kKeyMax) && ((double)d1 < kp.nearest_sq) && c < (surf ? Ts : Tc);
+        int i1 = -1, i2 = -1, i3 = -1;
+        if (found) {
+          i1 = c;
+          const float4 s = pb.sel[i];
+          if (surf) {
+            if (sm.sortedS) walk_warp<true>(s, c, tgtS, Ts, sm.rsS, fwdS, nearf, i2, i3);
+            else { if (lane == 0) walk_seq<true>(s, c, tgtS, Ts, fwdS, nearf, i2, i3); }
+          } else {
+            if (sm.sortedC) walk_warp<false>(s, c, tgtC, Tc, sm.rsC, fwdC, nearf, i2, i3);
+            else { if (lane == 0) walk_seq<false>(s, c, tgtC, Tc, fwdC, nearf, i2, i3); }
+          }
+        }
+        if (lane == 0) {
+          pb.pos[3 * i] = i1; pb.pos[3 * i + 1] = i2; pb.pos[3 * i + 2] = i3;
+          const int gq = q0 + i;
+          if (surf) { int* o = bv.ind_s + 3 * (size_t)(qs0 + gq); o[0] = i1; o[1] = i2; o[2] = i3; }
+          else { int* o = bv.ind_c + 2 * (size_t)(qc0 + gq - ns); o[0] = i1; o[1] = i2; }
+        }
+      }
+    } else if (!fast || ntot > bv.qtile) {
+      // iter % ICP_FREQ != 0: reuse pointSearch*Ind (StateEstimator.hpp:844, :970) — original indices from global
+      for (int i = threadIdx.x; i < nq; i += kThreads) {
+        const int gq = q0 + i;
+        if (i < nsT) { const int* o = bv.ind_s + 3 * (size_t)(qs0 + gq); pb.pos[3 * i] = o[0]; pb.pos[3 * i + 1] = o[1]; pb.pos[3 * i + 2] = o[2]; }
+        else { const int* o = bv.ind_c + 2 * (size_t)(qc0 + gq - ns); pb.pos[3 * i] = o[0]; pb.pos[3 * i + 1] = o[1]; pb.pos[3 * i + 2] = -1; }
+      }
+    }
+    __syncthreads();
+    LINS_TICK(5);
+    // ---- A5/A6 residuals + A7-A9 fold ------------------------------------------------------------------------------
+    // tripod points: fast path -> slots of the sorted copies; otherwise original indices into the walk clouds.
+    // (fast path with several tiles on a non-search iteration falls back to original indices, see above)
+    const bool by_slot = fast && (search || ntot <= bv.qtile);
+    for (int i = threadIdx.x; i < nq; i += kThreads) {
+      const bool surf = i < nsT;
+      const int i1 = pb.pos[3 * i], i2 = pb.pos[3 * i + 1], i3 = pb.pos[3 * i + 2];
+      const float4 s = pb.sel[i];
+      float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool ok = false;
+      if (surf) {
+        if (i2 >= 0 && i3 >= 0 && i1 >= 0 && i1 < Ts && i2 < Ts && i3 < Ts) {
+          if (by_slot) ok = plane_residual(s, pb.azS[i1], pb.azS[i2], pb.azS[i3], weighted, coeff);
+          else ok = plane_residual(s, __ldg(&tgtS[i1]), __ldg(&tgtS[i2]), __ldg(&tgtS[i3]), weighted, coeff);
+        }
+      } else {
+        if (i2 >= 0 && i1 >= 0 && i1 < Tc && i2 < Tc) {
+          if (by_slot) ok = line_residual(s, pb.azC[i1], pb.azC[i2], weighted, coeff);
+          else ok = line_residual(s, __ldg(&tgtC[i1]), __ldg(&tgtC[i2]), weighted, coeff);
+        }
+      }
+      if (ok) {
+        if (MODE == MODE_ICP_REDUCE) accumulate_row_icp(pb.qpt[i], coeff, sm, kp.scan_period, acc);
+        else accumulate_row(pb.qpt[i], coeff, sm.R, kp.lidar_scale, acc);
+        if (surf) ++cntS; else ++cntC;
+      }
+      if (MODE == MODE_ASSOC) {
+        const int gq = q0 + i;
+        if (surf) {
+          const size_t o = (size_t)(qs0 + gq);
+          if (bv.sel_s) { bv.sel_s[3 * o] = s.x; bv.sel_s[3 * o + 1] = s.y; bv.sel_s[3 * o + 2] = s.z; }
+          if (bv.coeff_s) { bv.coeff_s[4 * o] = coeff.x; bv.coeff_s[4 * o + 1] = coeff.y; bv.coeff_s[4 * o + 2] = coeff.z; bv.coeff_s[4 * o + 3] = coeff.w; }
+          if (bv.mask_s) bv.mask_s[o] = ok ? 1 : 0;
+        } else {
+          const size_t o = (size_t)(qc0 + gq - ns);
+          if (bv.sel_c) { bv.sel_c[3 * o] = s.x; bv.sel_c[3 * o + 1] = s.y; bv.sel_c[3 * o + 2] = s.z; }
+          if (bv.coeff_c) { bv.coeff_c[4 * o] = coeff.x; bv.coeff_c[4 * o + 1] = coeff.y; bv.coeff_c[4 * o + 2] = coeff.z; bv.coeff_c[4 * o + 3] = coeff.w; }
+          if (bv.mask_c) bv.mask_c[o] = ok ? 1 : 0;
+        }
+      }
+    }
+  }
+  LINS_TICK(6);
+  block_reduce_acc(sm, acc, cntS, cntC);
+  LINS_TICK(7);
+}
+
+}  // namespace lins_dev

@@ -1,0 +1,270 @@
+// Association through a (ring, azimuth-bin) index — the fast path of rows A3/A4 (exact 1-NN + ring walks,
+// reference lins/include/StateEstimator.hpp:844-915 and :970-1029).
+//
+// Per scan, once: the target cloud (ring-sorted, as the reference's extractFeatures emits it, :727-826) is
+// bucket-sorted on device by  ring * nb + azimuth_bin  into a packed copy (x, y, z, bits(original index)) that
+// lives in SHARED memory when it fits (the VLP-16 case) and in a global scratch otherwise; the bucket table
+// always lives in shared memory.  This replaces pcl::KdTreeFLANN::setInputCloud (:363-364, :1158-1159).
+//
+// Per query, per iteration, one warp:
+//   every search is "the minimum of the exact f32 distance over a set of rings", and always comes with an upper
+//   bound U on that minimum (the distance to the previous iteration's answer while it is still an admissible
+//   candidate, else the 5 m gate NEAREST_FEATURE_SEARCH_SQ_DIST, which bounds every answer the reference can
+//   accept).  A target whose azimuth differs from the query's by D is at least rho_q * sin(min(D, pi/2)) away
+//   (rho_q = the query's distance from the z axis), so only the bins within
+//        asin(1.002 * sqrt(U) / rho_q) + 1e-5 rad          (the whole ring if sqrt(U) >= rho_q)
+//   of the query's azimuth can hold the minimum (or tie with it).  Those bins are one or two contiguous slices
+//   of the sorted copy per ring.  Keys are (distance bits, order) u64 exactly as in the plain walk, so ties
+//   resolve like the reference's "first strictly smaller wins" loops; the 1-NN key is (distance bits, original
+//   index): lowest index among exact ties.
+#pragma once
+#include "lins_kernels.cuh"
+
+namespace lins_dev {
+
+struct AzIndex {
+  const float4* pts;  // sorted copy (shared or global)
+  const int* bstart;  // [nrings * nb + 1], shared
+  int nb, nrings, T;
+};
+
+__device__ __forceinline__ int az_bin(float x, float y, int nb) {
+  const float a = atan2f(y, x);
+  int b = (int)floorf((a + kPiF) * ((float)nb * (0.5f / kPiF)));
+  return min(max(b, 0), nb - 1);
+}
+// bins per ring for a table of TAB entries
+__device__ __forceinline__ int az_bins_for(int nrings, int tab) {
+  int p2 = 1;
+  while (p2 < nrings) p2 <<= 1;
+  return tab / p2;
+}
+
+// counting sort of `src` (ring-sorted, rings validated by build_ring_table) into dst, table in bstart[0..TAB]
+template <int TAB>
+__device__ void az_build(const float4* __restrict__ src, int T, float4* dst, int* bstart, int* scan_tmp, int nb) {
+  for (int b = threadIdx.x; b <= TAB; b += kThreads) bstart[b] = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < T; j += kThreads) {
+    const float4 t = __ldg(&src[j]);
+    atomicAdd(&bstart[(int)t.w * nb + az_bin(t.x, t.y, nb)], 1);
+  }
+  __syncthreads();
+  constexpr int PER = TAB / kThreads;
+  static_assert(PER >= 1 && PER * kThreads == TAB, "table size must be a multiple of the block size");
+  int loc[PER];
+  int sum = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) { loc[k] = bstart[threadIdx.x * PER + k]; sum += loc[k]; }
+  scan_tmp[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    constexpr int PW = kThreads / 32;
+    int part[PW];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < PW; ++k) { part[k] = scan_tmp[threadIdx.x * PW + k]; s += part[k]; }
+    int incl = s;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, m); if ((int)threadIdx.x >= m) incl += o; }
+    int run = incl - s;
+#pragma unroll
+    for (int k = 0; k < PW; ++k) { const int v = part[k]; scan_tmp[threadIdx.x * PW + k] = run; run += v; }
+    if (threadIdx.x == 31) bstart[TAB] = incl;
+  }
+  __syncthreads();
+  {
+    int run = scan_tmp[threadIdx.x];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { bstart[threadIdx.x * PER + k] = run; run += loc[k]; }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < T; j += kThreads) {  // scatter; the counters double as cursors
+    const float4 t = __ldg(&src[j]);
+    const int pos = atomicAdd(&bstart[(int)t.w * nb + az_bin(t.x, t.y, nb)], 1);
+    dst[pos] = make_float4(t.x, t.y, t.z, __int_as_float(((int)t.w << 24) | j));  // ring (8 bits) | original index (24 bits)
+  }
+  __syncthreads();
+  {  // cursors hold bucket ENDS == next bucket's start: shift back by one bucket
+    int prev[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { const int b = threadIdx.x * PER + k; prev[k] = b == 0 ? 0 : bstart[b - 1]; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; ++k) bstart[threadIdx.x * PER + k] = prev[k];
+  }
+  __syncthreads();
+}
+
+// half-width (rad) of the azimuth window that can hold a target with squared distance <= U
+__device__ __forceinline__ float az_halfwidth(float U, float rho) {
+  const float r = sqrtf(U) * 1.002f + 1.0e-5f;
+  if (!(r < rho)) return 4.0f;  // > pi: the whole ring
+  return asinf(r / rho) + 1.0e-5f;
+}
+// bins [blo, blo + nbins) (mod nb) covering [aq - th, aq + th] plus one spare bin on each side
+__device__ __forceinline__ void az_window(int nb, float aq, float th, int& blo, int& nbins) {
+  const float inv_binw = (float)nb * (0.5f / kPiF);
+  nbins = (int)(2.0f * th * inv_binw) + 3;
+  if (!(th < kPiF) || nbins >= nb) { blo = 0; nbins = nb; return; }
+  int b = (int)floorf((aq - th + kPiF) * inv_binw) - 1;
+  b %= nb;
+  if (b < 0) b += nb;
+  blo = b;
+}
+
+__device__ __forceinline__ int slot_index(float w) { return __float_as_int(w) & 0x00ffffff; }
+__device__ __forceinline__ int slot_ring(float w) { return (int)((unsigned)__float_as_int(w) >> 24); }
+__device__ __forceinline__ int pack_window(int blo, int nbins) { return (blo << 16) | nbins; }
+
+// warp arg-min of u64 keys with a payload, through the redux unit (two 32-bit reductions instead of 15 shuffles)
+__device__ __forceinline__ void warp_argmin(unsigned long long& k, int& payload) {
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)(k & 0xffffffffu);
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  const unsigned win = __ballot_sync(0xffffffffu, hi == mhi && lo == mlo);
+  payload = __shfl_sync(0xffffffffu, payload, __ffs(win) - 1);
+  k = ((unsigned long long)mhi << 32) | mlo;
+}
+
+// ---- phase P1 (one THREAD per query): azimuth, range, bound and window of the closest-point search ------------
+// qa = (azimuth, rho, -, -); returns the packed window or -1 when the query cannot match anything
+__device__ __forceinline__ int az_prepare_nn(const AzIndex& ix, const float4 s, float nearf, int seed_slot, float4& qa) {
+  qa = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!(s.x == s.x && s.y == s.y && s.z == s.z) || ix.T <= 0) return -1;
+  const float aq = atan2f(s.y, s.x);
+  const float rho = sqrtf(__fadd_rn(__fmul_rn(s.x, s.x), __fmul_rn(s.y, s.y)));
+  float U1 = nearf;  // nothing beyond the gate can be accepted (StateEstimator.hpp:851)
+  if (seed_slot >= 0 && seed_slot < ix.T) {
+    const float4 t = ix.pts[seed_slot];
+    const float d = sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z);
+    if (d < U1) U1 = d;
+  }
+  int blo, nbins;
+  az_window(ix.nb, aq, az_halfwidth(U1, rho), blo, nbins);
+  qa.x = aq; qa.y = rho;
+  return pack_window(blo, nbins);
+}
+
+// ---- phase P2 (one WARP per query): exact 1-NN over all rings inside the window ---------------------------------
+// LPR lanes share one ring; two candidates per lane are in flight per trip (the scan is latency bound).
+template <int LPR>
+__device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4 s, int p, int pe, unsigned long long& best, int& bpos) {
+  for (; p < pe; p += 2 * LPR) {
+    const int pb2 = p + LPR;
+    const float4 t0 = ix.pts[p];
+    const float4 t1 = ix.pts[pb2 < pe ? pb2 : p];
+    const unsigned long long k0 = pack_key(sqdist_f32(s.x, s.y, s.z, t0.x, t0.y, t0.z), (unsigned)slot_index(t0.w));
+    const unsigned long long k1 = pack_key(sqdist_f32(s.x, s.y, s.z, t1.x, t1.y, t1.z), (unsigned)slot_index(t1.w));
+    if (k0 < best) { best = k0; bpos = p; }
+    if (pb2 < pe && k1 < best) { best = k1; bpos = pb2; }
+  }
+}
+template <int LPR>
+__device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, const float4 s, int win, int& pos) {
+  const int lane = threadIdx.x & 31;
+  const int blo = win >> 16, nbins = win & 0xffff;
+  constexpr int RPP = 32 / LPR;
+  const int sub = lane % LPR;
+  unsigned long long best = kKeyMax;
+  int bpos = -1;
+  const int e0 = min(blo + nbins, ix.nb), e1 = blo + nbins - ix.nb;
+  for (int rbase = 0; rbase < ix.nrings; rbase += RPP) {
+    const int r = rbase + lane / LPR;
+    if (r < ix.nrings) {
+      const int base = r * ix.nb;
+      az_scan_nn_slice<LPR>(ix, s, ix.bstart[base + blo] + sub, ix.bstart[base + e0], best, bpos);
+      if (e1 > 0) az_scan_nn_slice<LPR>(ix, s, ix.bstart[base] + sub, ix.bstart[base + e1], best, bpos);
+    }
+  }
+  warp_argmin(best, bpos);
+  if ((unsigned)(best >> 32) >= 0x7f800000u) { best = kKeyMax; bpos = -1; }  // only inf / NaN distances: nothing found
+  pos = bpos;
+  return best;
+}
+__device__ __forceinline__ unsigned long long az_scan_nn(const AzIndex& ix, const float4 s, int win, int& pos) {
+  if (ix.nrings <= 8) return az_scan_nn_t<4>(ix, s, win, pos);
+  if (ix.nrings <= 16) return az_scan_nn_t<2>(ix, s, win, pos);
+  return az_scan_nn_t<1>(ix, s, win, pos);
+}
+
+// ---- phase P3 (one THREAD per query): accept the closest point, bound + window the walks ------------------------
+// returns false when there is no closest point.  w2 / w3 = windows of the Ind2 / Ind3 searches, ccr = (cr << 24) | c
+template <bool SURF>
+__device__ __forceinline__ bool az_prepare_walk(const AzIndex& ix, const float4 s, const float4 qa, unsigned long long k1, int p1,
+                                                int seed2, int seed3, int fwdBound, float nearf, double nearest_sq,
+                                                int& w2, int& w3, int& ccr) {
+  const float d1 = __uint_as_float((unsigned)(k1 >> 32));
+  if (k1 == kKeyMax || !((double)d1 < nearest_sq) || p1 < 0) return false;
+  const int c = (int)(unsigned)(k1 & 0xffffffffu);
+  const int cr = slot_ring(ix.pts[p1].w);
+  // bounds from the previous answers while they are still admissible candidates of THIS search
+  float U2 = nearf, U3 = nearf;
+  if (seed2 >= 0 && seed2 < ix.T) {
+    const float4 t = ix.pts[seed2];
+    const int j = slot_index(t.w), r = slot_ring(t.w);
+    const bool ring_ok = SURF ? (r == cr) : (r != cr && r >= cr - 2 && r <= cr + 2);
+    if (ring_ok && j != c && (j < c || j < fwdBound)) { const float d = sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z); if (d < U2) U2 = d; }
+  }
+  if (SURF && seed3 >= 0 && seed3 < ix.T) {
+    const float4 t = ix.pts[seed3];
+    const int j = slot_index(t.w), r = slot_ring(t.w);
+    if (r != cr && r >= cr - 2 && r <= cr + 2 && (j < c || j < fwdBound)) { const float d = sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z); if (d < U3) U3 = d; }
+  }
+  int blo, nbins;
+  az_window(ix.nb, qa.x, az_halfwidth(U2, qa.y), blo, nbins);
+  w2 = pack_window(blo, nbins);
+  if (SURF) { az_window(ix.nb, qa.x, az_halfwidth(U3, qa.y), blo, nbins); w3 = pack_window(blo, nbins); } else w3 = w2;
+  ccr = (cr << 24) | c;
+  return true;
+}
+
+// ---- phase P4 (one WARP per query): the ring walks inside their windows -------------------------------------------
+// SURF: Ind2 over ring cr (window w2), Ind3 over rings cr-2, cr-1, cr+1, cr+2 (window w3).  Corner: Ind2 over rings
+// cr-2, cr-1, cr+1, cr+2 (window w2).  Forward candidates (original index j > c) count only while j < fwdBound.
+template <bool SURF>
+__device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
+                                             int& i2, int& i3, int& pos2, int& pos3) {
+  const int lane = threadIdx.x & 31;
+  const int c = ccr & 0x00ffffff, cr = (int)((unsigned)ccr >> 24);
+  const unsigned long long init = pack_key(nearf, 0u);
+  unsigned long long k2 = init, k3 = init;
+  int q2 = -1, q3 = -1;
+  const int r = cr - 2 + lane / 6, sub = lane % 6;  // 5 rings x 6 lanes
+  if (lane < 30 && r >= 0 && r < ix.nrings && (SURF || r != cr)) {
+    const bool cls2 = SURF ? (r == cr) : true;
+    const int win = cls2 ? w2 : w3;
+    const int blo = win >> 16, nbins = win & 0xffff, base = r * ix.nb;
+    for (int seg = 0; seg < 2; ++seg) {
+      int p, pe;
+      if (seg == 0) { p = ix.bstart[base + blo]; pe = ix.bstart[base + min(blo + nbins, ix.nb)]; }
+      else { const int e1 = blo + nbins - ix.nb; if (e1 <= 0) break; p = ix.bstart[base]; pe = ix.bstart[base + e1]; }
+      for (p += sub; p < pe; p += 12) {  // two candidates in flight per lane
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int pu = p + 6 * u;
+          const float4 t = ix.pts[pu < pe ? pu : p];
+          const int j = slot_index(t.w);
+          const bool fwd = j > c;
+          const unsigned long long k = pack_key(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z), fwd ? order_fwd(j) : order_bwd(j));
+          if (pu < pe && j != c && (!fwd || j < fwdBound)) {
+            if (cls2) { if (k < k2) { k2 = k; q2 = pu; } }
+            else { if (k < k3) { k3 = k; q3 = pu; } }
+          }
+        }
+      }
+    }
+  }
+  warp_argmin(k2, q2);
+  i2 = (k2 >= init || q2 < 0) ? -1 : order_decode((unsigned)(k2 & 0xffffffffu));
+  pos2 = i2 < 0 ? -1 : q2;
+  if (SURF) {
+    warp_argmin(k3, q3);
+    i3 = (k3 >= init || q3 < 0) ? -1 : order_decode((unsigned)(k3 & 0xffffffffu));
+    pos3 = i3 < 0 ? -1 : q3;
+  } else {
+    i3 = -1; pos3 = -1;
+  }
+}
+
+}  // namespace lins_dev

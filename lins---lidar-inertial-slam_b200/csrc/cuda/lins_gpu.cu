@@ -15,33 +15,41 @@
 
 #include "../host/math_utils.hpp"
 #include "../host/small_linalg.hpp"
-#include "lins_kernels.cuh"
+#include "lins_assoc.cuh"
 
 using namespace lins_dev;
 
 namespace {
 
 // ---------------------------------------------------------------------------------------------------------
-// dynamic shared memory layout: [qpt float4 x Q][sel float4 x Q][key u64 x Q][ind int x 3Q][Smem]
+// dynamic shared memory layout:
+//   [qpt float4 x Q][sel float4 x Q][qa float4 x Q][qw int4 x Q][key u64 x Q][pos int x 3Q][Smem][azS ..][azC ..]
+// cap_s / cap_c = points of the (ring, azimuth)-sorted target copies kept in shared memory (0: global scratch)
 // ---------------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t smem_bytes_for(int qtile) {
-  size_t b = (size_t)qtile * (16 + 16 + 8 + 12);
+__host__ __device__ inline size_t smem_front_bytes(int qtile) {
+  size_t b = (size_t)qtile * (16 + 16 + 16 + 16 + 8 + 12);
   b = (b + 15) & ~(size_t)15;
-  return b + sizeof(Smem) + 16;
+  return b + ((sizeof(Smem) + 15) & ~(size_t)15);
+}
+__host__ __device__ inline size_t smem_bytes_for(int qtile, int cap_s, int cap_c) {
+  return smem_front_bytes(qtile) + 16 * ((size_t)cap_s + (size_t)cap_c) + 16;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2) lins_ieskf_kernel(const __grid_constant__ BatchView bv,
+__global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_constant__ BatchView bv,
                                                               const __grid_constant__ KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int Q = bv.qtile;
   float4* qpt = reinterpret_cast<float4*>(smem_raw);
   float4* selbuf = qpt + Q;
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(selbuf + Q);
-  int* indbuf = reinterpret_cast<int*>(key + Q);
-  size_t off = (size_t)Q * (16 + 16 + 8 + 12);
+  float4* qabuf = selbuf + Q;
+  int4* qwbuf = reinterpret_cast<int4*>(qabuf + Q);
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(qwbuf + Q);
+  int* posbuf = reinterpret_cast<int*>(key + Q);
+  size_t off = (size_t)Q * (16 + 16 + 16 + 16 + 8 + 12);
   off = (off + 15) & ~(size_t)15;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + off);
+  float4* az_smem = reinterpret_cast<float4*>(smem_raw + smem_front_bytes(Q));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const double sig2 = kp.lidar_std * kp.lidar_std;
 
@@ -51,6 +59,9 @@ __global__ void __launch_bounds__(kThreads, 2) lins_ieskf_kernel(const __grid_co
     fence_mbar_init();
   }
   __syncthreads();
+
+  PassBuffers pb;
+  pb.qpt = qpt; pb.sel = selbuf; pb.qa = qabuf; pb.qw = qwbuf; pb.key = key; pb.pos = posbuf; pb.azS = nullptr; pb.azC = nullptr;
 
   for (;;) {
     if (tid == 0) { sm.scan = atomicAdd(bv.work_counter, 1); sm.tlast = clock64(); }
@@ -70,13 +81,23 @@ __global__ void __launch_bounds__(kThreads, 2) lins_ieskf_kernel(const __grid_co
       const int tc0 = bv.tc_off[scan], Tc = bv.tc_off[scan + 1] - tc0;
       build_ring_table(bv.ts + ts0, Ts, sm.rsS, &sm.sortedS);
       build_ring_table(bv.tc + tc0, Tc, sm.rsC, &sm.sortedC);
-      // the exact 1-NN index (≙ kdtree*->setInputCloud, StateEstimator.hpp:363-364 / :1158-1159), on device
-      const float4* nnS = bv.nn_s ? bv.nn_s + bv.nn_s_off[scan] : bv.ts + ts0;
-      const float4* nnC = bv.nn_c ? bv.nn_c + bv.nn_c_off[scan] : bv.tc + tc0;
-      const int TnS = bv.nn_s ? bv.nn_s_off[scan + 1] - bv.nn_s_off[scan] : Ts;
-      const int TnC = bv.nn_c ? bv.nn_c_off[scan + 1] - bv.nn_c_off[scan] : Tc;
-      grid_build<kHashS>(nnS, TnS, bv.grid_s + (bv.nn_s ? bv.nn_s_off[scan] : ts0), sm.bstartS, sm.scan_tmp);
-      grid_build<kHashC>(nnC, TnC, bv.grid_c + (bv.nn_c ? bv.nn_c_off[scan] : tc0), sm.bstartC, sm.scan_tmp);
+      // the search index (≙ kdtree*->setInputCloud, StateEstimator.hpp:363-364 / :1158-1159), built on device:
+      // (ring, azimuth-bin) counting sort of both clouds, into shared memory when they fit
+      if (tid == 0) {
+        const bool ok = sm.sortedS && sm.sortedC && bv.nn_s == nullptr && bv.nn_c == nullptr && Ts < (1 << 24) && Tc < (1 << 24);  // slot payload = ring (8 bits) | index (24 bits)
+        sm.az_ok = ok ? 1 : 0;
+        sm.nringsS = ok && Ts > 0 ? (int)bv.ts[ts0 + Ts - 1].w + 1 : 0;  // ring-sorted: the last point has the largest ring
+        sm.nringsC = ok && Tc > 0 ? (int)bv.tc[tc0 + Tc - 1].w + 1 : 0;
+        sm.nbS = az_bins_for(sm.nringsS, kAzTabS);
+        sm.nbC = az_bins_for(sm.nringsC, kAzTabC);
+      }
+      __syncthreads();
+      pb.azS = Ts <= bv.cap_s ? az_smem : bv.az_s + ts0;
+      pb.azC = Tc <= bv.cap_c ? az_smem + bv.cap_s : bv.az_c + tc0;
+      if (sm.az_ok) {
+        az_build<kAzTabS>(bv.ts + ts0, Ts, const_cast<float4*>(pb.azS), sm.azTabS, sm.scan_tmp, sm.nbS);
+        az_build<kAzTabC>(bv.tc + tc0, Tc, const_cast<float4*>(pb.azC), sm.azTabC, sm.scan_tmp, sm.nbC);
+      }
     }
     lins_report* rep = bv.reports ? bv.reports + scan : nullptr;
     int iters = 0;
@@ -85,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 2) lins_ieskf_kernel(const __grid_co
     if (MODE == MODE_ASSOC || MODE == MODE_ICP_REDUCE) {
       if (tid == 0) compute_iter_consts(sm);
       __syncthreads();
-      association_pass<MODE>(sm, bv, kp, scan, kp.iter0, qpt, selbuf, key, indbuf);
+      association_pass<MODE>(sm, bv, kp, scan, kp.iter0, pb, true);
       if (bv.accum) {
         if (tid < kNAcc) bv.accum[(size_t)scan * 32 + tid] = sm.acc[tid];
         if (tid == 32) { bv.accum[(size_t)scan * 32 + 28] = (double)sm.cnt[0]; bv.accum[(size_t)scan * 32 + 29] = (double)sm.cnt[1]; }
@@ -99,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 2) lins_ieskf_kernel(const __grid_co
       if (tid == 0) compute_iter_consts(sm);
       __syncthreads();
       LINS_TICK(1);
-      association_pass<MODE>(sm, bv, kp, scan, iter, qpt, selbuf, key, indbuf);
+      association_pass<MODE>(sm, bv, kp, scan, iter, pb, iter == 0);
       build_A6(sm);
       if (tid == 128) box_minus(sm);
       __syncthreads();
@@ -220,11 +241,12 @@ __global__ void __launch_bounds__(kThreads, 2) lins_ieskf_kernel(const __grid_co
 // the 3 / 2 matched targets (16 B each), recomputes de-skew, residual, weight and Jacobian row, and reduces
 // the 28 sums per scan with a fixed shuffle tree.  Nothing is staged in shared memory: with >= 4096 resident
 // scans the working set exceeds L2 and the kernel is bound by HBM traffic + f64 issue.
-__global__ void __launch_bounds__(kThreads) lins_jacobian_kernel(const __grid_constant__ BatchView bv,
+constexpr int kJacThreads = 256;
+__global__ void __launch_bounds__(kJacThreads) lins_jacobian_kernel(const __grid_constant__ BatchView bv,
                                                                  const __grid_constant__ KParams kp) {
   const int lane = threadIdx.x & 31;
-  const int warps_per_grid = (gridDim.x * kThreads) >> 5;
-  for (int scan = (blockIdx.x * kThreads + threadIdx.x) >> 5; scan < bv.n_scans; scan += warps_per_grid) {
+  const int warps_per_grid = (gridDim.x * kJacThreads) >> 5;
+  for (int scan = (blockIdx.x * kJacThreads + threadIdx.x) >> 5; scan < bv.n_scans; scan += warps_per_grid) {
     // per-scan constants (every lane computes the same values)
     const double* st = bv.state_in + (size_t)scan * 20;
     double rn[3] = {st[0], st[1], st[2]};
@@ -355,7 +377,8 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   int n = 0;
   size_t nqs = 0, nqc = 0, nts = 0, ntc = 0;
   int max_q = 0;
-  DevBuf<float4> qs, qc, ts, tc, grid_s, grid_c;
+  DevBuf<float4> qs, qc, ts, tc, az_s, az_c;
+  int max_ts = 0, max_tc = 0;
   DevBuf<int> qs_off, qc_off, ts_off, tc_off, ind_s, ind_c, counter;
   DevBuf<long long> timers;
   DevBuf<double> state_in, cov_in, state_out, cov_out, accum;
@@ -369,7 +392,7 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   PinBuf<lins_scan_result> h_results;
   PinBuf<lins_report> h_reports;
   void release() {
-    qs.release(); qc.release(); ts.release(); tc.release(); grid_s.release(); grid_c.release(); qs_off.release(); qc_off.release(); ts_off.release();
+    qs.release(); qc.release(); ts.release(); tc.release(); az_s.release(); az_c.release(); qs_off.release(); qc_off.release(); ts_off.release();
     tc_off.release(); ind_s.release(); ind_c.release(); counter.release(); state_in.release(); cov_in.release();
     state_out.release(); cov_out.release(); accum.release(); results.release(); reports.release(); sel_s.release();
     sel_c.release(); coeff_s.release(); coeff_c.release(); mask_s.release(); mask_c.release(); h_pts.release();
@@ -439,8 +462,14 @@ int validate_params(const lins_params* p) {
 }
 
 template <int MODE>
-int launch_mode(lins_ctx* ctx, const BatchView& bv, const KParams& kp) {
-  size_t smem = smem_bytes_for(bv.qtile);
+int launch_mode(lins_ctx* ctx, const BatchView& bv_in, const KParams& kp) {
+  BatchView bv = bv_in;
+  // keep the sorted target copies in shared memory when they fit; the corner copy is small and goes first
+  if ((int)smem_bytes_for(bv.qtile, bv.cap_s, bv.cap_c) > ctx->max_smem_optin) {
+    if ((int)smem_bytes_for(bv.qtile, 0, bv.cap_c) <= ctx->max_smem_optin) bv.cap_s = 0;
+    else { bv.cap_s = 0; bv.cap_c = 0; }
+  }
+  size_t smem = smem_bytes_for(bv.qtile, bv.cap_s, bv.cap_c);
   if ((int)smem > ctx->max_smem_optin) return fail(ctx, LINS_E_TOOBIG, "query tile does not fit shared memory");
   CK(cudaFuncSetAttribute(lins_ieskf_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
@@ -477,8 +506,8 @@ int reserve_outputs(lins_ctx* ctx, Resident& r, bool want_reports, bool want_tra
   CK(r.cov_out.reserve((size_t)r.n * 324));
   CK(r.results.reserve(r.n));
   CK(r.accum.reserve((size_t)r.n * 32));
-  CK(r.grid_s.reserve(r.nts + 4));
-  CK(r.grid_c.reserve(r.ntc + 4));
+  CK(r.az_s.reserve(r.nts + 4));
+  CK(r.az_c.reserve(r.ntc + 4));
   CK(r.ind_s.reserve(3 * r.nqs + 4));
   CK(r.ind_c.reserve(2 * r.nqc + 4));
   CK(r.counter.reserve(4));
@@ -500,7 +529,8 @@ BatchView view_of(const Resident& r, bool reports, bool trace) {
   bv.state_in = r.state_in.p; bv.cov_in = r.cov_in.p; bv.state_out = r.state_out.p; bv.cov_out = r.cov_out.p;
   bv.results = r.results.p; bv.reports = reports ? r.reports.p : nullptr;
   bv.ind_s = r.ind_s.p; bv.ind_c = r.ind_c.p;
-  bv.grid_s = r.grid_s.p; bv.grid_c = r.grid_c.p;
+  bv.az_s = r.az_s.p; bv.az_c = r.az_c.p;
+  bv.cap_s = r.max_ts; bv.cap_c = r.max_tc;  // launch_mode() zeroes what does not fit shared memory
   if (trace) {
     bv.sel_s = r.sel_s.p; bv.sel_c = r.sel_c.p; bv.coeff_s = r.coeff_s.p; bv.coeff_c = r.coeff_c.p;
     bv.mask_s = r.mask_s.p; bv.mask_c = r.mask_c.p;
@@ -536,6 +566,7 @@ int stage_single(lins_ctx* ctx, const lins_point* surf_flat, int ns, const lins_
   CK(cudaMemcpyAsync(r.cov_in.p, r.h_cov.p, sizeof(double) * 324, cudaMemcpyHostToDevice, ctx->stream));
   r.nts = (size_t)std::max(std::max(ctx->map_ns, ctx->tree_ns), 0);
   r.ntc = (size_t)std::max(std::max(ctx->map_nc, ctx->tree_nc), 0);
+  r.max_ts = std::max(ctx->map_ns, 0); r.max_tc = std::max(ctx->map_nc, 0);
   int rc = reserve_outputs(ctx, r, true, trace);
   return rc;
 }
@@ -701,8 +732,12 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
   }
   if (!b->state_in || !b->cov_in) return fail(ctx, LINS_E_INVALID, "null prior");
   r.nqs = offs[0][n]; r.nqc = offs[1][n]; r.nts = offs[2][n]; r.ntc = offs[3][n];
-  r.max_q = 0;
-  for (int i = 0; i < n; ++i) r.max_q = std::max(r.max_q, (offs[0][i + 1] - offs[0][i]) + (offs[1][i + 1] - offs[1][i]));
+  r.max_q = 0; r.max_ts = 0; r.max_tc = 0;
+  for (int i = 0; i < n; ++i) {
+    r.max_q = std::max(r.max_q, (offs[0][i + 1] - offs[0][i]) + (offs[1][i + 1] - offs[1][i]));
+    r.max_ts = std::max(r.max_ts, offs[2][i + 1] - offs[2][i]);
+    r.max_tc = std::max(r.max_tc, offs[3][i + 1] - offs[3][i]);
+  }
   const size_t total = r.nqs + r.nqc + r.nts + r.ntc;
   CK(r.h_pts.reserve(total + 1)); CK(r.h_off.reserve(4 * (size_t)(n + 1)));
   CK(r.h_state.reserve((size_t)n * 20)); CK(r.h_cov.reserve((size_t)n * 324));
@@ -839,9 +874,9 @@ int lins_gpu_batch_jacobian_pass(lins_ctx* ctx, double* accum_out) {
   bv.state_in = r.state_out.p;  // linearise at the updated state; IDs = the last iteration's
   KParams kp = make_kparams(ctx->prm, MODE_JACOBIAN, 1);
   const int warps_needed = r.n;
-  int grid = std::min((warps_needed + kWarps - 1) / kWarps, ctx->sm_count * 8);
+  int grid = std::min((warps_needed + (kJacThreads / 32) - 1) / (kJacThreads / 32), ctx->sm_count * 8);
   if (grid < 1) grid = 1;
-  lins_jacobian_kernel<<<grid, kThreads, 0, ctx->stream>>>(bv, kp);
+  lins_jacobian_kernel<<<grid, kJacThreads, 0, ctx->stream>>>(bv, kp);
   CK(cudaGetLastError());
   ctx->launches += 1;
   if (accum_out) {

@@ -20,18 +20,15 @@
 
 namespace lins_dev {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;   // one 16-warp CTA per SM: the per-scan index + target copy take most of its shared memory (1024 threads = 64 regs: spills, measured 2x slower)
 constexpr int kWarps = kThreads / 32;
 constexpr int kRingTab = 260;   // ring-start table: first target index with ring >= r, r = 0..259
 constexpr int kMaxRing = 256;   // rings outside [0, kMaxRing) or unsorted clouds take the sequential walk
 constexpr int kNAcc = 28;       // 21 (sym 6x6) + 6 (g*r) + 1 (r*r)
 constexpr int kNNChunk = 1024;  // targets per brute-force work item
-// exact 1-NN index: 2-D (x,y) spatial hash, cell edge kCell metres, rebuilt per scan on device
-constexpr int kHashS = 4096;    // buckets, surf targets
-constexpr int kHashC = 1024;    // buckets, corner targets
-constexpr float kCell = 0.5f;
-constexpr float kInvCell = 2.0f;
-constexpr int kGridRounds = 3;  // Chebyshev rings searched before the brute-force fallback
+constexpr int kAzTabS = 4096;   // (ring, azimuth bin) table entries, surf targets (see lins_assoc_az.cuh)
+constexpr int kAzTabC = 1024;   // corner targets
+constexpr float kPiF = 3.14159265358979f;
 constexpr unsigned long long kKeyMax = 0xFFFFFFFFFFFFFFFFull;
 
 enum KernelMode { MODE_IESKF = 0, MODE_ASSOC = 1, MODE_ICP_REDUCE = 2, MODE_JACOBIAN = 3 };
@@ -58,8 +55,9 @@ struct BatchView {
   float* coeff_s; float* coeff_c;        // optional (4 per query)
   unsigned char* mask_s; unsigned char* mask_c;  // optional
   double* accum;                         // n x 32 : 28 accumulators + m_surf + m_corner (modes 2,3)
-  float4* grid_s; float4* grid_c;        // scratch: bucket-sorted copies (x,y,z,bits(orig index)) of the 1-NN clouds,
-                                         // same per-scan offsets as the clouds they index
+  float4* az_s; float4* az_c;            // global scratch for the (ring, azimuth)-sorted copies when they do not fit
+                                         // shared memory; same per-scan offsets as ts / tc
+  int cap_s, cap_c;                      // points of the sorted copies held in shared memory (0 = use the scratch)
   int* work_counter;
   long long* timers;                     // optional: per-phase SM cycles summed over CTAs (diagnostics), 32 slots
   int qtile;                             // queries staged per pass
@@ -114,10 +112,11 @@ struct Smem {
   int sortedS, sortedC;
   int rsS[kRingTab];
   int rsC[kRingTab];
-  int bstartS[kHashS + 1];  // bucket -> first slot in grid_s (exclusive scan of the bucket histogram)
-  int bstartC[kHashC + 1];
+  int azTabS[kAzTabS + 1];  // (ring, azimuth bin) -> first slot of the sorted surf copy
+  int azTabC[kAzTabC + 1];
   int scan_tmp[kThreads];
-  int nlist;                // queries whose 1-NN is not yet proven exact
+  int az_ok;                // 1: both clouds ring-sorted + indexed (fast path); 0: legacy brute-force / plain walks
+  int nbS, nbC, nringsS, nringsC;
   unsigned long long mbar;
   unsigned int phase;
   long long tlast;
@@ -197,178 +196,6 @@ __device__ void nn_brute(const float4* sel, unsigned long long* key, int nq, con
   }
 }
 
-
-// ---- exact 1-NN through a 2-D spatial hash ------------------------------------------------------------------
-// cell(p) = (floor(x / kCell), floor(y / kCell)); z is ignored, so a cell is a vertical column.  Any target within
-// (real) distance < r * kCell of the query lies in a cell whose coordinates differ by at most r from the
-// query's, so after all cells of the Chebyshev rings 0..r have been examined the running minimum d is the
-// exact 1-NN as soon as d <= (r * kCell)^2 * (1 - 1e-4)  (the margin dwarfs every f32 rounding involved).
-// Hash collisions only add candidates; every candidate is evaluated with the exact f32 distance expression
-// and packed as (distance bits, original index), so the u64 minimum is "smallest distance, lowest index"
-// regardless of visiting order.  Queries still unproven after kGridRounds rings take the brute-force scan.
-__device__ __forceinline__ int cell_of(float v) {
-  float c = floorf(v * kInvCell);
-  c = fminf(fmaxf(c, -1.0e6f), 1.0e6f);  // monotone clamp; NaN -> -1e6 (such points are never indexed)
-  return (int)c;
-}
-__device__ __forceinline__ unsigned int cell_hash(int ix, int iy) {
-  return ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u);
-}
-
-// Build: histogram -> exclusive scan -> scatter.  src = the cloud the reference's kd-tree was built on.
-template <int H>
-__device__ void grid_build(const float4* __restrict__ src, int T, float4* __restrict__ sorted, int* bstart, int* scan_tmp) {
-  for (int b = threadIdx.x; b <= H; b += kThreads) bstart[b] = 0;
-  __syncthreads();
-  for (int j = threadIdx.x; j < T; j += kThreads) {
-    const float4 t = __ldg(&src[j]);
-    if (!(isfinite(t.x) && isfinite(t.y) && isfinite(t.z))) continue;  // PCL drops non-finite points
-    atomicAdd(&bstart[cell_hash(cell_of(t.x), cell_of(t.y)) & (H - 1)], 1);
-  }
-  __syncthreads();
-  // exclusive scan of H counters: each thread owns H / kThreads consecutive buckets
-  constexpr int PER = H / kThreads;
-  int loc[PER];
-  int sum = 0;
-#pragma unroll
-  for (int k = 0; k < PER; ++k) { loc[k] = bstart[threadIdx.x * PER + k]; sum += loc[k]; }
-  scan_tmp[threadIdx.x] = sum;
-  __syncthreads();
-  if (threadIdx.x < 32) {  // 256 partial sums, 8 per lane
-    int part[kThreads / 32];
-    int s = 0;
-#pragma unroll
-    for (int k = 0; k < kThreads / 32; ++k) { part[k] = scan_tmp[threadIdx.x * (kThreads / 32) + k]; s += part[k]; }
-    int incl = s;
-#pragma unroll
-    for (int m = 1; m < 32; m <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, m); if ((int)threadIdx.x >= m) incl += o; }
-    int run = incl - s;
-#pragma unroll
-    for (int k = 0; k < kThreads / 32; ++k) { int v = part[k]; scan_tmp[threadIdx.x * (kThreads / 32) + k] = run; run += v; }
-    if (threadIdx.x == 31) bstart[H] = incl;
-  }
-  __syncthreads();
-  {
-    int run = scan_tmp[threadIdx.x];
-#pragma unroll
-    for (int k = 0; k < PER; ++k) { bstart[threadIdx.x * PER + k] = run; run += loc[k]; }
-  }
-  __syncthreads();
-  // scatter with per-bucket cursors (the counters double as cursors, restored afterwards)
-  for (int j = threadIdx.x; j < T; j += kThreads) {
-    const float4 t = __ldg(&src[j]);
-    if (!(isfinite(t.x) && isfinite(t.y) && isfinite(t.z))) continue;
-    const int pos = atomicAdd(&bstart[cell_hash(cell_of(t.x), cell_of(t.y)) & (H - 1)], 1);
-    sorted[pos] = make_float4(t.x, t.y, t.z, __int_as_float(j));
-  }
-  __syncthreads();
-  // cursors now hold the END of each bucket == start of the next: shift back
-  {
-    int prev[PER];
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int b = threadIdx.x * PER + k;
-      prev[k] = b == 0 ? 0 : bstart[b - 1];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PER; ++k) bstart[threadIdx.x * PER + k] = prev[k];
-  }
-  __syncthreads();
-}
-
-// (dx,dy) of the k-th cell of Chebyshev ring r (r >= 1: 8r cells; r == 0: the centre)
-__device__ __forceinline__ void ring_cell(int r, int k, int& dx, int& dy) {
-  if (r == 0) { dx = 0; dy = 0; return; }
-  const int side = k / (2 * r), pos = k - side * 2 * r;
-  if (side == 0) { dx = -r + pos; dy = -r; }
-  else if (side == 1) { dx = r; dy = -r + pos; }
-  else if (side == 2) { dx = r - pos; dy = r; }
-  else { dx = -r; dy = r - pos; }
-}
-
-// brute-force scan of ALL targets for the listed queries: one warp per query, coalesced 16-B loads
-__device__ void nn_brute_listed(const float4* sel, unsigned long long* key, const int* list, int nlist,
-                                const float4* __restrict__ tgt, int T) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int li = warp; li < nlist; li += kWarps) {
-    const int qi = list[li];
-    const float4 s = sel[qi];
-    unsigned long long best = kKeyMax;
-    for (int j = lane; j < T; j += 32) {
-      const float4 t = __ldg(&tgt[j]);
-      const float d = sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z);
-      if (d < __int_as_float(0x7f800000)) { const unsigned long long k = pack_key(d, (unsigned)j); best = k < best ? k : best; }
-    }
-    best = warp_min_u64(best);
-    if (lane == 0) key[qi] = best;  // the full scan supersedes whatever the grid rounds found
-  }
-}
-
-template <int H>
-__device__ void nn_grid(Smem& sm, const float4* sel, unsigned long long* key, int nq, const float4* sorted,
-                        const int* bstart, const float4* __restrict__ tgt, int T, int* list) {
-  // round 0+1: centre cell + ring 1 (9 cells) for every query
-  for (int item = threadIdx.x; item < nq * 9; item += kThreads) {
-    const int qi = item / 9, k = item - qi * 9;
-    const float4 s = sel[qi];
-    const int cx = cell_of(s.x) + (k % 3) - 1, cy = cell_of(s.y) + (k / 3) - 1;
-    const unsigned b = cell_hash(cx, cy) & (H - 1);
-    unsigned long long best = kKeyMax;
-    for (int p = bstart[b], e = bstart[b + 1]; p < e; ++p) {
-      const float4 t = sorted[p];
-      const float d = sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z);
-      if (d < __int_as_float(0x7f800000)) { const unsigned long long kk = pack_key(d, (unsigned)__float_as_int(t.w)); best = kk < best ? kk : best; }
-    }
-    if (best != kKeyMax) atomicMin(&key[qi], best);
-  }
-  if (threadIdx.x == 0) sm.nlist = 0;
-  __syncthreads();
-  // classify: proven iff d <= (1 * kCell)^2 * (1 - 1e-4)
-  {
-    const float thr = kCell * kCell * 0.9999f;
-    for (int qi = threadIdx.x; qi < nq; qi += kThreads) {
-      const unsigned long long k1 = key[qi];
-      const float d = __uint_as_float((unsigned)(k1 >> 32));
-      if (!(k1 != kKeyMax && d <= thr)) list[atomicAdd(&sm.nlist, 1)] = qi;
-    }
-  }
-  __syncthreads();
-  for (int r = 2; r <= kGridRounds && sm.nlist > 0; ++r) {
-    const int nl = sm.nlist, ncell = 8 * r;
-    for (int item = threadIdx.x; item < nl * ncell; item += kThreads) {
-      const int li = item / ncell, k = item - li * ncell;
-      const int qi = list[li];
-      const float4 s = sel[qi];
-      int dx, dy;
-      ring_cell(r, k, dx, dy);
-      const unsigned b = cell_hash(cell_of(s.x) + dx, cell_of(s.y) + dy) & (H - 1);
-      unsigned long long best = kKeyMax;
-      for (int p = bstart[b], e = bstart[b + 1]; p < e; ++p) {
-        const float4 t = sorted[p];
-        const float d = sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z);
-        if (d < __int_as_float(0x7f800000)) { const unsigned long long kk = pack_key(d, (unsigned)__float_as_int(t.w)); best = kk < best ? kk : best; }
-      }
-      if (best != kKeyMax) atomicMin(&key[qi], best);
-    }
-    __syncthreads();
-    // compact the list in place (order irrelevant): one thread does it serially (lists are short)
-    if (threadIdx.x == 0) {
-      const float thr = (r * kCell) * (r * kCell) * 0.9999f;
-      int w = 0;
-      for (int li = 0; li < nl; ++li) {
-        const int qi = list[li];
-        const unsigned long long k1 = key[qi];
-        const float d = __uint_as_float((unsigned)(k1 >> 32));
-        if (!(k1 != kKeyMax && d <= thr)) list[w++] = qi;
-      }
-      sm.nlist = w;
-    }
-    __syncthreads();
-  }
-  if (sm.nlist > 0) nn_brute_listed(sel, key, list, sm.nlist, tgt, T);
-  __syncthreads();
-}
 
 // walk keys: high 32 = f32 distance bits, low 32 = visiting order (forward walk ascending j first, then the
 // backward walk descending j) so that u64 min == "first strictly smaller wins" of the reference loops.
@@ -700,146 +527,6 @@ __device__ void box_plus(Smem& sm) {
   q4 dq = axis2Quat(mk3(u[6], u[7], u[8]));
   q4 r = qnormalized(qmul(q, dq));
   l[6] = r.x; l[7] = r.y; l[8] = r.z; l[9] = r.w;
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// One association + reduction pass over all queries of the scan at the current linearisation point.
-// Fills sm.acc (28 sums) and sm.cnt (accepted surf / corner counts).
-template <int MODE>
-__device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& kp, int scan, int iter, float4* qpt,
-                                 float4* selbuf, unsigned long long* key, int* indbuf) {
-  const int qs0 = bv.qs_off[scan], ns = bv.qs_off[scan + 1] - qs0;
-  const int qc0 = bv.qc_off[scan], nc = bv.qc_off[scan + 1] - qc0;
-  const int ts0 = bv.ts_off[scan], Ts = bv.ts_off[scan + 1] - ts0;
-  const int tc0 = bv.tc_off[scan], Tc = bv.tc_off[scan + 1] - tc0;
-  const float4* __restrict__ tgtS = bv.ts + ts0;
-  const float4* __restrict__ tgtC = bv.tc + tc0;
-  const float4* __restrict__ nnS = bv.nn_s ? bv.nn_s + bv.nn_s_off[scan] : tgtS;
-  const float4* __restrict__ nnC = bv.nn_c ? bv.nn_c + bv.nn_c_off[scan] : tgtC;
-  const int TnS = bv.nn_s ? bv.nn_s_off[scan + 1] - bv.nn_s_off[scan] : Ts;
-  const int TnC = bv.nn_c ? bv.nn_c_off[scan + 1] - bv.nn_c_off[scan] : Tc;
-  const float4* gridS = bv.grid_s + (bv.nn_s ? bv.nn_s_off[scan] : ts0);
-  const float4* gridC = bv.grid_c + (bv.nn_c ? bv.nn_c_off[scan] : tc0);
-  const bool search = (iter % kp.icp_freq) == 0;
-  const bool weighted = iter >= kp.icp_freq;
-  const float nearf = (float)kp.nearest_sq;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  double acc[kNAcc];
-#pragma unroll
-  for (int k = 0; k < kNAcc; ++k) acc[k] = 0.0;
-  int cntS = 0, cntC = 0;
-
-  const int ntot = ns + nc;
-  for (int q0 = 0; q0 < ntot; q0 += bv.qtile) {
-    const int nq = min(bv.qtile, ntot - q0);
-    // sub-lists of this tile: surf [0, nsT) then corner [nsT, nq)
-    const int nsT = max(0, min(ns - q0, nq));
-    // ---- stage the tile's queries (1-D TMA) --------------------------------------------------------------
-    __syncthreads();  // previous tile fully consumed
-    if (threadIdx.x == 0) {
-      uint32_t bytes = 0;
-      if (nsT > 0) bytes += (uint32_t)nsT * 16u;
-      if (nq - nsT > 0) bytes += (uint32_t)(nq - nsT) * 16u;
-      fence_proxy_async();
-      mbar_expect_tx(&sm.mbar, bytes);
-      if (nsT > 0) tma_load_1d(qpt, bv.qs + qs0 + q0, (uint32_t)nsT * 16u, &sm.mbar);
-      if (nq - nsT > 0) tma_load_1d(qpt + nsT, bv.qc + qc0 + max(0, q0 - ns), (uint32_t)(nq - nsT) * 16u, &sm.mbar);
-    }
-    {
-      const unsigned int ph = sm.phase;  // one mbarrier phase per staged tile
-      mbar_wait(&sm.mbar, ph & 1u);
-      __syncthreads();
-      if (threadIdx.x == 0) sm.phase = ph + 1u;
-    }
-    LINS_TICK(2);
-    // ---- A2: de-skew -------------------------------------------------------------------------------------
-    for (int i = threadIdx.x; i < nq; i += kThreads) {
-      selbuf[i] = transform_to_start(qpt[i], sm, kp.scan_period);
-      key[i] = kKeyMax;
-    }
-    __syncthreads();
-    LINS_TICK(3);
-    if (search) {
-      // ---- A3/A4: exact 1-NN ------------------------------------------------------------------------------
-      if (nsT > 0 && TnS > 0) nn_grid<kHashS>(sm, selbuf, key, nsT, gridS, sm.bstartS, nnS, TnS, indbuf);
-      if (nq - nsT > 0 && TnC > 0) nn_grid<kHashC>(sm, selbuf + nsT, key + nsT, nq - nsT, gridC, sm.bstartC, nnC, TnC, indbuf);
-      __syncthreads();
-      LINS_TICK(4);
-      // ---- ring walks ---------------------------------------------------------------------------------------
-      const int fwdS = min(ns, Ts), fwdC = min(nc, Tc);  // :859 / :983 loop-bound quirk (+ OOB clamp)
-      for (int i = warp; i < nq; i += kWarps) {
-        const bool surf = i < nsT;
-        const unsigned long long k1 = key[i];
-        const float d1 = __uint_as_float((unsigned)(k1 >> 32));
-        const int c = (int)(unsigned)(k1 & 0xffffffffu);
-        const bool found = (k1 != kKeyMax) && ((double)d1 < kp.nearest_sq) && c < (surf ? Ts : Tc);
-        int i1 = -1, i2 = -1, i3 = -1;
-        if (found) {
-          i1 = c;
-          const float4 s = selbuf[i];
-          if (surf) {
-            if (sm.sortedS) walk_warp<true>(s, c, tgtS, Ts, sm.rsS, fwdS, nearf, i2, i3);
-            else { if (lane == 0) walk_seq<true>(s, c, tgtS, Ts, fwdS, nearf, i2, i3); }
-          } else {
-            if (sm.sortedC) walk_warp<false>(s, c, tgtC, Tc, sm.rsC, fwdC, nearf, i2, i3);
-            else { if (lane == 0) walk_seq<false>(s, c, tgtC, Tc, fwdC, nearf, i2, i3); }
-          }
-        }
-        if (lane == 0) {
-          indbuf[3 * i] = i1; indbuf[3 * i + 1] = i2; indbuf[3 * i + 2] = i3;
-          const int gq = q0 + i;
-          if (surf) { int* o = bv.ind_s + 3 * (size_t)(qs0 + gq); o[0] = i1; o[1] = i2; o[2] = i3; }
-          else { int* o = bv.ind_c + 2 * (size_t)(qc0 + gq - ns); o[0] = i1; o[1] = i2; }
-        }
-      }
-    } else {
-      // iter % ICP_FREQ != 0: reuse pointSearch*Ind (StateEstimator.hpp:844, :970)
-      for (int i = threadIdx.x; i < nq; i += kThreads) {
-        const int gq = q0 + i;
-        if (i < nsT) { const int* o = bv.ind_s + 3 * (size_t)(qs0 + gq); indbuf[3 * i] = o[0]; indbuf[3 * i + 1] = o[1]; indbuf[3 * i + 2] = o[2]; }
-        else { const int* o = bv.ind_c + 2 * (size_t)(qc0 + gq - ns); indbuf[3 * i] = o[0]; indbuf[3 * i + 1] = o[1]; indbuf[3 * i + 2] = -1; }
-      }
-    }
-    __syncthreads();
-    LINS_TICK(5);
-    // ---- A5/A6 residuals + A7-A9 fold ----------------------------------------------------------------------
-    for (int i = threadIdx.x; i < nq; i += kThreads) {
-      const bool surf = i < nsT;
-      const int i1 = indbuf[3 * i], i2 = indbuf[3 * i + 1], i3 = indbuf[3 * i + 2];
-      const float4 s = selbuf[i];
-      float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-      bool ok = false;
-      if (surf) {
-        if (i2 >= 0 && i3 >= 0 && i1 >= 0 && i1 < Ts && i2 < Ts && i3 < Ts)
-          ok = plane_residual(s, __ldg(&tgtS[i1]), __ldg(&tgtS[i2]), __ldg(&tgtS[i3]), weighted, coeff);
-      } else {
-        if (i2 >= 0 && i1 >= 0 && i1 < Tc && i2 < Tc) ok = line_residual(s, __ldg(&tgtC[i1]), __ldg(&tgtC[i2]), weighted, coeff);
-      }
-      if (ok) {
-        if (MODE == MODE_ICP_REDUCE) accumulate_row_icp(qpt[i], coeff, sm, kp.scan_period, acc);
-        else accumulate_row(qpt[i], coeff, sm.R, kp.lidar_scale, acc);
-        if (surf) ++cntS; else ++cntC;
-      }
-      if (MODE == MODE_ASSOC) {
-        const int gq = q0 + i;
-        if (surf) {
-          const size_t o = (size_t)(qs0 + gq);
-          if (bv.sel_s) { bv.sel_s[3 * o] = s.x; bv.sel_s[3 * o + 1] = s.y; bv.sel_s[3 * o + 2] = s.z; }
-          if (bv.coeff_s) { bv.coeff_s[4 * o] = coeff.x; bv.coeff_s[4 * o + 1] = coeff.y; bv.coeff_s[4 * o + 2] = coeff.z; bv.coeff_s[4 * o + 3] = coeff.w; }
-          if (bv.mask_s) bv.mask_s[o] = ok ? 1 : 0;
-        } else {
-          const size_t o = (size_t)(qc0 + gq - ns);
-          if (bv.sel_c) { bv.sel_c[3 * o] = s.x; bv.sel_c[3 * o + 1] = s.y; bv.sel_c[3 * o + 2] = s.z; }
-          if (bv.coeff_c) { bv.coeff_c[4 * o] = coeff.x; bv.coeff_c[4 * o + 1] = coeff.y; bv.coeff_c[4 * o + 2] = coeff.z; bv.coeff_c[4 * o + 3] = coeff.w; }
-          if (bv.mask_c) bv.mask_c[o] = ok ? 1 : 0;
-        }
-      }
-    }
-  }
-  LINS_TICK(6);
-  block_reduce_acc(sm, acc, cntS, cntC);
-  LINS_TICK(7);
 }
 
 }  // namespace lins_dev
