@@ -18,6 +18,9 @@ struct PassBuffers {
                              //               legacy path: original indices
   float4* qa;                // fast path: (azimuth, rho, -, -) of the de-skewed query
   int4* qw;                  // fast path: search windows w1 / w2 / w3 and (ring << 24 | index) of the closest point
+  float4* qref;              // fast path: pointSel at the last closest-point search + the slack (m) of its answer
+  float4* qref2;             // fast path: pointSel at the last walk search + the slack of Ind2 / Ind3
+  int* qccr;                 // fast path: (ring << 24 | original index) of the closest point, -1 = none
   const float4* azS;         // sorted copies (shared or global)
   const float4* azC;
 };
@@ -85,49 +88,81 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
     if (search && fast) {
       // ---- A3/A4 fast path, four short phases.  Scalar preparation (atan2f, asinf, bounds) runs one THREAD per
       // query so that all queries proceed in parallel; the memory scans run one WARP per query.
+      // per-query level: -2 everything certified, -3 closest point certified (walks only), >= 0 full search (= window),
+      // -1 cannot match
       for (int i = threadIdx.x; i < nq; i += kThreads) {  // P1
-        float4 qa;
+        const float4 s = pb.sel[i];
         const bool surf = i < nsT;
-        const int w1 = az_prepare_nn(surf ? ixS : ixC, pb.sel[i], nearf, seeded ? pb.pos[3 * i] : -1, qa);
+        float4 qa = make_float4(0.f, 0.f, -1.f, 0.f);
+        if (seeded) {  // certificates: displaced by less than half the slack since the search => same answer
+          const float4 r1 = pb.qref[i], r2 = pb.qref2[i];
+          const bool ok1 = r1.w > 0.f && 2.0f * sqrtf(sqdist_f32(s.x, s.y, s.z, r1.x, r1.y, r1.z)) + 2.0e-4f < r1.w;
+          const bool ok2 = r2.w > 0.f && 2.0f * sqrtf(sqdist_f32(s.x, s.y, s.z, r2.x, r2.y, r2.z)) + 2.0e-4f < r2.w;
+          if (ok1 && (ok2 || pb.qccr[i] < 0)) { pb.qw[i] = make_int4(-2, 0, 0, 0); continue; }
+          if (ok1) { az_polar(s, qa); pb.qa[i] = qa; pb.qw[i] = make_int4(-3, 0, 0, 0); continue; }
+        }
+        const int w1 = az_prepare_nn(surf ? ixS : ixC, s, nearf, seeded ? pb.pos[3 * i] : -1, qa);
         pb.qa[i] = qa;
         pb.qw[i] = make_int4(w1, 0, 0, 0);
       }
       __syncthreads();
+      const float gate = sqrtf(nearf);
       for (int i = warp; i < nq; i += kWarps) {  // P2
         const int w1 = pb.qw[i].x;
+        if (w1 < -1) continue;  // closest point certified
         unsigned long long k1 = kKeyMax;
+        unsigned second = 0xffffffffu;
         int p1 = -1;
-        if (w1 >= 0) k1 = az_scan_nn(i < nsT ? ixS : ixC, pb.sel[i], w1, p1);
-        if (lane == 0) { pb.key[i] = k1; pb.pos[3 * i] = p1; }
+        const bool surf = i < nsT;
+        if (w1 >= 0) k1 = az_scan_nn(surf ? ixS : ixC, pb.sel[i], w1, p1, second);
+        if (lane == 0) {
+          const float d1 = __uint_as_float((unsigned)(k1 >> 32));
+          const bool acc1 = k1 != kKeyMax && p1 >= 0 && (double)d1 < kp.nearest_sq;
+          const float4 s = pb.sel[i];
+          pb.qref[i] = make_float4(s.x, s.y, s.z, w1 >= 0 ? search_slack((unsigned)(k1 >> 32), second, pb.qa[i].w, gate, acc1) : -1.f);
+          pb.pos[3 * i] = acc1 ? p1 : -1;
+          pb.qccr[i] = acc1 ? ((slot_ring((surf ? ixS : ixC).pts[p1].w) << 24) | (int)(unsigned)(k1 & 0xffffffffu)) : -1;
+        }
       }
       __syncthreads();
       LINS_TICK(4);
       for (int i = threadIdx.x; i < nq; i += kThreads) {  // P3
+        const int lvl = pb.qw[i].x;
+        if (lvl == -2) continue;
         const bool surf = i < nsT;
         const int gq = q0 + i;
-        int w2 = 0, w3 = 0, ccr = 0;
-        const int sd2 = seeded ? pb.pos[3 * i + 1] : -1, sd3 = seeded ? pb.pos[3 * i + 2] : -1;
-        bool found;
-        if (surf) found = az_prepare_walk<true>(ixS, pb.sel[i], pb.qa[i], pb.key[i], pb.pos[3 * i], sd2, sd3, fwdS, nearf, kp.nearest_sq, w2, w3, ccr);
-        else found = az_prepare_walk<false>(ixC, pb.sel[i], pb.qa[i], pb.key[i], pb.pos[3 * i], sd2, sd3, fwdC, nearf, kp.nearest_sq, w2, w3, ccr);
-        pb.qw[i] = make_int4(found ? 1 : -1, w2, w3, ccr);
-        if (!found) {
-          pb.pos[3 * i] = -1; pb.pos[3 * i + 1] = -1; pb.pos[3 * i + 2] = -1;
+        const int ccr = pb.qccr[i];
+        if (ccr < 0) {  // no closest point within the gate: nothing to walk
+          pb.pos[3 * i + 1] = -1; pb.pos[3 * i + 2] = -1;
+          pb.qw[i] = make_int4(-1, 0, 0, 0);
           if (surf) { int* o = bv.ind_s + 3 * (size_t)(qs0 + gq); o[0] = -1; o[1] = -1; o[2] = -1; }
           else { int* o = bv.ind_c + 2 * (size_t)(qc0 + gq - ns); o[0] = -1; o[1] = -1; }
+          continue;
         }
+        int w2 = 0, w3 = 0;
+        float B2 = 0.f, B3 = 0.f;
+        const int sd2 = seeded ? pb.pos[3 * i + 1] : -1, sd3 = seeded ? pb.pos[3 * i + 2] : -1;
+        const int c = ccr & 0x00ffffff, cr = (int)((unsigned)ccr >> 24);
+        if (surf) az_prepare_walk<true>(ixS, pb.sel[i], pb.qa[i], c, cr, sd2, sd3, fwdS, nearf, w2, w3, B2, B3);
+        else az_prepare_walk<false>(ixC, pb.sel[i], pb.qa[i], c, cr, sd2, sd3, fwdC, nearf, w2, w3, B2, B3);
+        pb.qw[i] = make_int4(1, w2, w3, ccr);
+        reinterpret_cast<float2*>(pb.key)[i] = make_float2(B2, B3);
       }
       __syncthreads();
       for (int i = warp; i < nq; i += kWarps) {  // P4
         const int4 w = pb.qw[i];
-        if (w.x < 0) continue;
+        if (w.x < 0) continue;  // certified (-2) or no closest point (-1)
         const bool surf = i < nsT;
         const int gq = q0 + i;
+        const float2 B = reinterpret_cast<const float2*>(pb.key)[i];
         int i2, i3, p2, p3;
-        if (surf) az_scan_walk<true>(ixS, pb.sel[i], w.w, w.y, w.z, fwdS, nearf, i2, i3, p2, p3);
-        else az_scan_walk<false>(ixC, pb.sel[i], w.w, w.y, w.z, fwdC, nearf, i2, i3, p2, p3);
+        float slack;
+        if (surf) az_scan_walk<true>(ixS, pb.sel[i], w.w, w.y, w.z, fwdS, nearf, B.x, B.y, i2, i3, p2, p3, slack);
+        else az_scan_walk<false>(ixC, pb.sel[i], w.w, w.y, w.z, fwdC, nearf, B.x, B.y, i2, i3, p2, p3, slack);
         if (lane == 0) {
           pb.pos[3 * i + 1] = p2; pb.pos[3 * i + 2] = p3;
+          const float4 s = pb.sel[i];
+          pb.qref2[i] = make_float4(s.x, s.y, s.z, slack);
           const int i1 = w.w & 0x00ffffff;
           if (surf) { int* o = bv.ind_s + 3 * (size_t)(qs0 + gq); o[0] = i1; o[1] = i2; o[2] = i3; }
           else { int* o = bv.ind_c + 2 * (size_t)(qc0 + gq - ns); o[0] = i1; o[1] = i2; }

@@ -17,6 +17,14 @@
 //   of the sorted copy per ring.  Keys are (distance bits, order) u64 exactly as in the plain walk, so ties
 //   resolve like the reference's "first strictly smaller wins" loops; the 1-NN key is (distance bits, original
 //   index): lowest index among exact ties.
+//
+// Certificates.  Every search also returns how much room its answer has: the runner-up's distance (or the
+// distance bound of everything outside the window, whichever is smaller) minus the winner's, and the winner's
+// distance to the 5 m gate.  While the query has moved less than half of the smallest such slack since that
+// search (true distances change by at most the displacement), neither the argmin nor any gate decision can
+// change, so the stored answer is reused and the search is skipped.  Exact ties have slack 0 and are therefore
+// re-searched every iteration.  Windows are built for sqrt(U) + kCertMargin so the "outside" bound is not vacuous.
+// The closest point and the walks are certified separately (a new closest point always forces new walks).
 #pragma once
 #include "lins_kernels.cuh"
 
@@ -116,6 +124,17 @@ __device__ __forceinline__ void az_window(int nb, float aq, float th, int& blo, 
 __device__ __forceinline__ int slot_index(float w) { return __float_as_int(w) & 0x00ffffff; }
 __device__ __forceinline__ int slot_ring(float w) { return (int)((unsigned)__float_as_int(w) >> 24); }
 __device__ __forceinline__ int pack_window(int blo, int nbins) { return (blo << 16) | nbins; }
+constexpr float kCertMargin = 0.1f;  // metres added to every search radius so that certificates have room
+// bound used to build a window: (sqrt(U) + margin)^2
+__device__ __forceinline__ float widen(float U) { const float r = sqrtf(U) + kCertMargin; return r * r; }
+// slack (metres) of one search: winner / runner-up as f32 squared-distance BITS (0xffffffff = none), Bout = distance
+// bound of everything not examined, gate = sqrt(NEAREST_FEATURE_SEARCH_SQ_DIST).  Negative = cannot be certified.
+__device__ __forceinline__ float search_slack(unsigned best_bits, unsigned second_bits, float Bout, float gate, bool accepted) {
+  const float db = best_bits >= 0x7f800000u ? Bout : fminf(sqrtf(__uint_as_float(best_bits)), Bout);
+  if (!accepted) return db - gate * 1.00001f;                      // stays "nothing within the gate"
+  const float ds = second_bits >= 0x7f800000u ? Bout : fminf(sqrtf(__uint_as_float(second_bits)), Bout);
+  return fminf(ds - db, gate * 0.99999f - db);                     // stays the winner, stays inside the gate
+}
 
 // warp arg-min of u64 keys with a payload, through the redux unit (two 32-bit reductions instead of 15 shuffles)
 __device__ __forceinline__ void warp_argmin(unsigned long long& k, int& payload) {
@@ -128,76 +147,96 @@ __device__ __forceinline__ void warp_argmin(unsigned long long& k, int& payload)
 }
 
 // ---- phase P1 (one THREAD per query): azimuth, range, bound and window of the closest-point search ------------
-// qa = (azimuth, rho, -, -); returns the packed window or -1 when the query cannot match anything
+// qa = (azimuth, rho, -, outside bound B1); returns the packed window or -1 when the query cannot match anything
+__device__ __forceinline__ void az_polar(const float4 s, float4& qa) {
+  qa.x = atan2f(s.y, s.x);
+  qa.y = sqrtf(__fadd_rn(__fmul_rn(s.x, s.x), __fmul_rn(s.y, s.y)));
+}
 __device__ __forceinline__ int az_prepare_nn(const AzIndex& ix, const float4 s, float nearf, int seed_slot, float4& qa) {
-  qa = make_float4(0.f, 0.f, 0.f, 0.f);
+  qa = make_float4(0.f, 0.f, -1.f, 0.f);
   if (!(s.x == s.x && s.y == s.y && s.z == s.z) || ix.T <= 0) return -1;
-  const float aq = atan2f(s.y, s.x);
-  const float rho = sqrtf(__fadd_rn(__fmul_rn(s.x, s.x), __fmul_rn(s.y, s.y)));
+  az_polar(s, qa);
+  const float aq = qa.x, rho = qa.y;
   float U1 = nearf;  // nothing beyond the gate can be accepted (StateEstimator.hpp:851)
   if (seed_slot >= 0 && seed_slot < ix.T) {
     const float4 t = ix.pts[seed_slot];
     const float d = sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z);
     if (d < U1) U1 = d;
   }
+  const float Uw = widen(U1);
   int blo, nbins;
-  az_window(ix.nb, aq, az_halfwidth(U1, rho), blo, nbins);
-  qa.x = aq; qa.y = rho;
+  az_window(ix.nb, aq, az_halfwidth(Uw, rho), blo, nbins);
+  qa.w = nbins >= ix.nb ? 3.0e38f : sqrtf(Uw);  // everything outside the window is farther than this
   return pack_window(blo, nbins);
 }
 
 // ---- phase P2 (one WARP per query): exact 1-NN over all rings inside the window ---------------------------------
 // LPR lanes share one ring; two candidates per lane are in flight per trip (the scan is latency bound).
+// (best, second): the lane's smallest key and the distance bits of its runner-up
+__device__ __forceinline__ void take(unsigned long long k, int p, unsigned long long& best, unsigned& second, int& bpos) {
+  if (k < best) { second = (unsigned)(best >> 32); best = k; bpos = p; }
+  else { const unsigned d = (unsigned)(k >> 32); second = d < second ? d : second; }
+}
 template <int LPR>
-__device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4 s, int p, int pe, unsigned long long& best, int& bpos) {
+__device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4 s, int p, int pe, unsigned long long& best,
+                                                 unsigned& second, int& bpos) {
   for (; p < pe; p += 2 * LPR) {
     const int pb2 = p + LPR;
     const float4 t0 = ix.pts[p];
     const float4 t1 = ix.pts[pb2 < pe ? pb2 : p];
     const unsigned long long k0 = pack_key(sqdist_f32(s.x, s.y, s.z, t0.x, t0.y, t0.z), (unsigned)slot_index(t0.w));
     const unsigned long long k1 = pack_key(sqdist_f32(s.x, s.y, s.z, t1.x, t1.y, t1.z), (unsigned)slot_index(t1.w));
-    if (k0 < best) { best = k0; bpos = p; }
-    if (pb2 < pe && k1 < best) { best = k1; bpos = pb2; }
+    take(k0, p, best, second, bpos);
+    if (pb2 < pe) take(k1, pb2, best, second, bpos);
   }
 }
+// warp arg-min that also yields the distance bits of the overall runner-up
+__device__ __forceinline__ void warp_argmin2(unsigned long long& best, unsigned& second, int& payload) {
+  const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)(best & 0xffffffffu);
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  const unsigned wmask = __ballot_sync(0xffffffffu, hi == mhi && lo == mlo);
+  const int wl = __ffs(wmask) - 1;
+  const bool winner = (int)(threadIdx.x & 31) == wl;
+  second = __reduce_min_sync(0xffffffffu, winner ? second : hi);  // every other lane's best is a runner-up candidate
+  payload = __shfl_sync(0xffffffffu, payload, wl);
+  best = ((unsigned long long)mhi << 32) | mlo;
+}
 template <int LPR>
-__device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, const float4 s, int win, int& pos) {
+__device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, const float4 s, int win, int& pos, unsigned& second_out) {
   const int lane = threadIdx.x & 31;
   const int blo = win >> 16, nbins = win & 0xffff;
   constexpr int RPP = 32 / LPR;
   const int sub = lane % LPR;
   unsigned long long best = kKeyMax;
+  unsigned second = 0xffffffffu;
   int bpos = -1;
   const int e0 = min(blo + nbins, ix.nb), e1 = blo + nbins - ix.nb;
   for (int rbase = 0; rbase < ix.nrings; rbase += RPP) {
     const int r = rbase + lane / LPR;
     if (r < ix.nrings) {
       const int base = r * ix.nb;
-      az_scan_nn_slice<LPR>(ix, s, ix.bstart[base + blo] + sub, ix.bstart[base + e0], best, bpos);
-      if (e1 > 0) az_scan_nn_slice<LPR>(ix, s, ix.bstart[base] + sub, ix.bstart[base + e1], best, bpos);
+      az_scan_nn_slice<LPR>(ix, s, ix.bstart[base + blo] + sub, ix.bstart[base + e0], best, second, bpos);
+      if (e1 > 0) az_scan_nn_slice<LPR>(ix, s, ix.bstart[base] + sub, ix.bstart[base + e1], best, second, bpos);
     }
   }
-  warp_argmin(best, bpos);
+  warp_argmin2(best, second, bpos);
   if ((unsigned)(best >> 32) >= 0x7f800000u) { best = kKeyMax; bpos = -1; }  // only inf / NaN distances: nothing found
   pos = bpos;
+  second_out = second;
   return best;
 }
-__device__ __forceinline__ unsigned long long az_scan_nn(const AzIndex& ix, const float4 s, int win, int& pos) {
-  if (ix.nrings <= 8) return az_scan_nn_t<4>(ix, s, win, pos);
-  if (ix.nrings <= 16) return az_scan_nn_t<2>(ix, s, win, pos);
-  return az_scan_nn_t<1>(ix, s, win, pos);
+__device__ __forceinline__ unsigned long long az_scan_nn(const AzIndex& ix, const float4 s, int win, int& pos, unsigned& second) {
+  if (ix.nrings <= 8) return az_scan_nn_t<4>(ix, s, win, pos, second);
+  if (ix.nrings <= 16) return az_scan_nn_t<2>(ix, s, win, pos, second);
+  return az_scan_nn_t<1>(ix, s, win, pos, second);
 }
 
-// ---- phase P3 (one THREAD per query): accept the closest point, bound + window the walks ------------------------
-// returns false when there is no closest point.  w2 / w3 = windows of the Ind2 / Ind3 searches, ccr = (cr << 24) | c
+// ---- phase P3 (one THREAD per query): bound + window the walks of a query whose closest point is (c, cr) -------
+// w2 / w3 = windows of the Ind2 / Ind3 searches, B2 / B3 = distance bound of everything outside them
 template <bool SURF>
-__device__ __forceinline__ bool az_prepare_walk(const AzIndex& ix, const float4 s, const float4 qa, unsigned long long k1, int p1,
-                                                int seed2, int seed3, int fwdBound, float nearf, double nearest_sq,
-                                                int& w2, int& w3, int& ccr) {
-  const float d1 = __uint_as_float((unsigned)(k1 >> 32));
-  if (k1 == kKeyMax || !((double)d1 < nearest_sq) || p1 < 0) return false;
-  const int c = (int)(unsigned)(k1 & 0xffffffffu);
-  const int cr = slot_ring(ix.pts[p1].w);
+__device__ __forceinline__ void az_prepare_walk(const AzIndex& ix, const float4 s, const float4 qa, int c, int cr, int seed2,
+                                                int seed3, int fwdBound, float nearf, int& w2, int& w3, float& B2, float& B3) {
   // bounds from the previous answers while they are still admissible candidates of THIS search
   float U2 = nearf, U3 = nearf;
   if (seed2 >= 0 && seed2 < ix.T) {
@@ -212,11 +251,16 @@ __device__ __forceinline__ bool az_prepare_walk(const AzIndex& ix, const float4 
     if (r != cr && r >= cr - 2 && r <= cr + 2 && (j < c || j < fwdBound)) { const float d = sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z); if (d < U3) U3 = d; }
   }
   int blo, nbins;
-  az_window(ix.nb, qa.x, az_halfwidth(U2, qa.y), blo, nbins);
+  const float Uw2 = widen(U2);
+  az_window(ix.nb, qa.x, az_halfwidth(Uw2, qa.y), blo, nbins);
   w2 = pack_window(blo, nbins);
-  if (SURF) { az_window(ix.nb, qa.x, az_halfwidth(U3, qa.y), blo, nbins); w3 = pack_window(blo, nbins); } else w3 = w2;
-  ccr = (cr << 24) | c;
-  return true;
+  B2 = nbins >= ix.nb ? 3.0e38f : sqrtf(Uw2);
+  if (SURF) {
+    const float Uw3 = widen(U3);
+    az_window(ix.nb, qa.x, az_halfwidth(Uw3, qa.y), blo, nbins);
+    w3 = pack_window(blo, nbins);
+    B3 = nbins >= ix.nb ? 3.0e38f : sqrtf(Uw3);
+  } else { w3 = w2; B3 = B2; }
 }
 
 // ---- phase P4 (one WARP per query): the ring walks inside their windows -------------------------------------------
@@ -224,11 +268,14 @@ __device__ __forceinline__ bool az_prepare_walk(const AzIndex& ix, const float4 
 // cr-2, cr-1, cr+1, cr+2 (window w2).  Forward candidates (original index j > c) count only while j < fwdBound.
 template <bool SURF>
 __device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
-                                             int& i2, int& i3, int& pos2, int& pos3) {
+                                             float B2, float B3, int& i2, int& i3, int& pos2, int& pos3, float& slack) {
   const int lane = threadIdx.x & 31;
   const int c = ccr & 0x00ffffff, cr = (int)((unsigned)ccr >> 24);
-  const unsigned long long init = pack_key(nearf, 0u);
-  unsigned long long k2 = init, k3 = init;
+  // keys are NOT gated here: the minimum over the candidates is needed even when it lies beyond the gate (to certify
+  // "still nothing within the gate"); the gate is applied to the reduced winner, which is equivalent to the
+  // reference's `pointSqDis < minPointSqDis` starting from NEAREST_FEATURE_SEARCH_SQ_DIST.
+  unsigned long long k2 = kKeyMax, k3 = kKeyMax;
+  unsigned s2 = 0xffffffffu, s3 = 0xffffffffu;
   int q2 = -1, q3 = -1;
   const int r = cr - 2 + lane / 6, sub = lane % 6;  // 5 rings x 6 lanes
   if (lane < 30 && r >= 0 && r < ix.nrings && (SURF || r != cr)) {
@@ -248,20 +295,26 @@ __device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, 
           const bool fwd = j > c;
           const unsigned long long k = pack_key(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z), fwd ? order_fwd(j) : order_bwd(j));
           if (pu < pe && j != c && (!fwd || j < fwdBound)) {
-            if (cls2) { if (k < k2) { k2 = k; q2 = pu; } }
-            else { if (k < k3) { k3 = k; q3 = pu; } }
+            if (cls2) take(k, pu, k2, s2, q2);
+            else take(k, pu, k3, s3, q3);
           }
         }
       }
     }
   }
-  warp_argmin(k2, q2);
-  i2 = (k2 >= init || q2 < 0) ? -1 : order_decode((unsigned)(k2 & 0xffffffffu));
-  pos2 = i2 < 0 ? -1 : q2;
+  const float gate = sqrtf(nearf);
+  const unsigned nearbits = __float_as_uint(nearf);
+  warp_argmin2(k2, s2, q2);
+  const bool ok2 = (unsigned)(k2 >> 32) < nearbits && q2 >= 0;
+  i2 = ok2 ? order_decode((unsigned)(k2 & 0xffffffffu)) : -1;
+  pos2 = ok2 ? q2 : -1;
+  slack = search_slack((unsigned)(k2 >> 32), s2, B2, gate, ok2);
   if (SURF) {
-    warp_argmin(k3, q3);
-    i3 = (k3 >= init || q3 < 0) ? -1 : order_decode((unsigned)(k3 & 0xffffffffu));
-    pos3 = i3 < 0 ? -1 : q3;
+    warp_argmin2(k3, s3, q3);
+    const bool ok3 = (unsigned)(k3 >> 32) < nearbits && q3 >= 0;
+    i3 = ok3 ? order_decode((unsigned)(k3 & 0xffffffffu)) : -1;
+    pos3 = ok3 ? q3 : -1;
+    slack = fminf(slack, search_slack((unsigned)(k3 >> 32), s3, B3, gate, ok3));
   } else {
     i3 = -1; pos3 = -1;
   }

@@ -23,11 +23,11 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------------------
 // dynamic shared memory layout:
-//   [qpt float4 x Q][sel float4 x Q][qa float4 x Q][qw int4 x Q][key u64 x Q][pos int x 3Q][Smem][azS ..][azC ..]
+//   [qpt float4 x Q][sel float4 x Q][qa float4 x Q][qw int4 x Q][qref, qref2 float4 x Q][key u64 x Q][pos int x 3Q][qccr int x Q][pos int x 3Q][Smem][azS ..][azC ..]
 // cap_s / cap_c = points of the (ring, azimuth)-sorted target copies kept in shared memory (0: global scratch)
 // ---------------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t smem_front_bytes(int qtile) {
-  size_t b = (size_t)qtile * (16 + 16 + 16 + 16 + 8 + 12);
+  size_t b = (size_t)qtile * (16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4);
   b = (b + 15) & ~(size_t)15;
   return b + ((sizeof(Smem) + 15) & ~(size_t)15);
 }
@@ -44,9 +44,12 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
   float4* selbuf = qpt + Q;
   float4* qabuf = selbuf + Q;
   int4* qwbuf = reinterpret_cast<int4*>(qabuf + Q);
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(qwbuf + Q);
+  float4* qrefbuf = reinterpret_cast<float4*>(qwbuf + Q);
+  float4* qref2buf = qrefbuf + Q;
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(qref2buf + Q);
   int* posbuf = reinterpret_cast<int*>(key + Q);
-  size_t off = (size_t)Q * (16 + 16 + 16 + 16 + 8 + 12);
+  int* qccrbuf = posbuf + 3 * Q;
+  size_t off = (size_t)Q * (16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4);
   off = (off + 15) & ~(size_t)15;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + off);
   float4* az_smem = reinterpret_cast<float4*>(smem_raw + smem_front_bytes(Q));
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
   __syncthreads();
 
   PassBuffers pb;
-  pb.qpt = qpt; pb.sel = selbuf; pb.qa = qabuf; pb.qw = qwbuf; pb.key = key; pb.pos = posbuf; pb.azS = nullptr; pb.azC = nullptr;
+  pb.qpt = qpt; pb.sel = selbuf; pb.qa = qabuf; pb.qw = qwbuf; pb.qref = qrefbuf; pb.qref2 = qref2buf; pb.qccr = qccrbuf; pb.key = key; pb.pos = posbuf; pb.azS = nullptr; pb.azC = nullptr;
 
   for (;;) {
     if (tid == 0) { sm.scan = atomicAdd(bv.work_counter, 1); sm.tlast = clock64(); }
