@@ -52,10 +52,9 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
   ixS.pts = pb.azS; ixS.bstart = sm.azTabS; ixS.nb = sm.nbS; ixS.nrings = sm.nringsS; ixS.T = Ts;
   ixC.pts = pb.azC; ixC.bstart = sm.azTabC; ixC.nb = sm.nbC; ixC.nrings = sm.nringsC; ixC.T = Tc;
 
-  double acc[kNAcc];
-#pragma unroll
-  for (int k = 0; k < kNAcc; ++k) acc[k] = 0.0;
-  int cntS = 0, cntC = 0;
+  if (threadIdx.x < kNAcc) sm.acc[threadIdx.x] = 0.0;
+  if (threadIdx.x == 32) { sm.cnt[0] = 0; sm.cnt[1] = 0; }
+  // (ordered before the first block_reduce_acc by the barriers of the tile loop)
 
   for (int q0 = 0; q0 < ntot; q0 += bv.qtile) {
     const int nq = min(bv.qtile, ntot - q0);
@@ -213,6 +212,11 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
     // tripod points: fast path -> slots of the sorted copies; otherwise original indices into the walk clouds.
     // (fast path with several tiles on a non-search iteration falls back to original indices, see above)
     const bool by_slot = fast && (search || ntot <= bv.qtile);
+    // the 28 f64 accumulators live only here, so they do not take registers away from the search phases
+    double acc[kNAcc];
+#pragma unroll
+    for (int k = 0; k < kNAcc; ++k) acc[k] = 0.0;
+    int cntS = 0, cntC = 0;
     for (int i = threadIdx.x; i < nq; i += kThreads) {
       const bool surf = i < nsT;
       const int i1 = pb.pos[3 * i], i2 = pb.pos[3 * i + 1], i3 = pb.pos[3 * i + 2];
@@ -250,9 +254,9 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         }
       }
     }
+    LINS_TICK(6);
+    block_reduce_acc(sm, acc, cntS, cntC);
   }
-  LINS_TICK(6);
-  block_reduce_acc(sm, acc, cntS, cntC);
   LINS_TICK(7);
 }
 

@@ -388,13 +388,13 @@ __device__ void block_reduce_acc(Smem& sm, double* acc, int cs, int cc) {
   for (int m = 16; m > 0; m >>= 1) { cs += __shfl_xor_sync(0xffffffffu, cs, m); cc += __shfl_xor_sync(0xffffffffu, cc, m); }
   if (lane == 0) { sm.wcnt[warp][0] = cs; sm.wcnt[warp][1] = cc; }
   __syncthreads();
-  if (threadIdx.x < kNAcc) {
-    double v = 0;
+  if (threadIdx.x < kNAcc) {  // accumulates: callers zero sm.acc / sm.cnt at the start of a pass
+    double v = sm.acc[threadIdx.x];
     for (int w = 0; w < kWarps; ++w) v += sm.wacc[w][threadIdx.x];
     sm.acc[threadIdx.x] = v;
   }
   if (threadIdx.x == 32) {
-    int a = 0, b = 0;
+    int a = sm.cnt[0], b = sm.cnt[1];
     for (int w = 0; w < kWarps; ++w) { a += sm.wcnt[w][0]; b += sm.wcnt[w][1]; }
     sm.cnt[0] = a; sm.cnt[1] = b;
   }
