@@ -748,7 +748,7 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
   CK(r.qs_off.reserve(n + 1)); CK(r.qc_off.reserve(n + 1)); CK(r.ts_off.reserve(n + 1)); CK(r.tc_off.reserve(n + 1));
   CK(r.state_in.reserve((size_t)n * 20)); CK(r.cov_in.reserve((size_t)n * 324));
   // pack 32-B PointXYZI -> 16-B float4 while copying into pinned staging (the copy is needed anyway: user
-  // buffers are pageable), so PCIe moves half the bytes.  The pack is spread over host threads in ~1 M-point
+  // buffers are pageable), so PCIe moves half the bytes.  The pack is spread over host threads in 64 K-point
   // slices; each slice's H2D copy is queued as soon as the slice is packed, so packing and PCIe overlap.
   float4* hp = r.h_pts.p;
   size_t seg[5] = {0, r.nqs, r.nqs + r.nqc, r.nqs + r.nqc + r.nts, total};
@@ -757,7 +757,7 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
   {
     struct Slice { int k; size_t a, b; };
     std::vector<Slice> slices;
-    const size_t SL = 1u << 18;
+    const size_t SL = 1u << 16;
     for (int k = 0; k < 4; ++k)
       for (size_t a = 0; a < seg[k + 1] - seg[k]; a += SL) slices.push_back(Slice{k, a, std::min(a + SL, seg[k + 1] - seg[k])});
     std::atomic<size_t> next(0);
@@ -776,7 +776,8 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
       }
     };
     unsigned hw = std::thread::hardware_concurrency();
-    int nthr = (int)std::min<size_t>(std::min<unsigned>(hw ? hw : 4, 16), std::max<size_t>(slices.size(), 1));
+    int nthr = (int)std::min<size_t>(std::min<unsigned>(hw ? hw / 2 : 4, 32), std::max<size_t>(slices.size(), 1));
+    if (nthr < 1) nthr = 1;
     std::vector<std::thread> th;
     for (int t = 1; t < nthr; ++t) th.emplace_back(worker);
     worker();

@@ -105,3 +105,54 @@ def generate(config="config3", n=1, seed0=1, threads=None, **overrides):
         return Batch(clouds, offsets, state, cov, truth, extra)
     finally:
         L.lins_synth_batch_destroy(h)
+
+
+# ---- offline sequence driver (tools/synth/lins_sequence.cpp): the C++ StateEstimator shim on a synthetic drive ----
+_SEQ = None
+
+
+def seq_lib():
+    global _SEQ
+    if _SEQ is None:
+        path = os.path.join(_DIR, "liblins_seq.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-s", "-C", _DIR, "seq"])
+        L = C.CDLL(path)
+        L.lins_seq_run.restype = C.c_void_p
+        L.lins_seq_run.argtypes = [C.POINTER(SynthCfg), C.c_uint64, C.c_int, C.c_int]
+        L.lins_seq_destroy.argtypes = [C.c_void_p]
+        L.lins_seq_num_units.argtypes = [C.c_void_p]
+        L.lins_seq_num_scans.argtypes = [C.c_void_p]
+        L.lins_seq_desc.argtypes = [C.c_void_p, C.POINTER(LinsBatchDesc)]
+        L.lins_seq_array.restype = C.POINTER(C.c_double)
+        L.lins_seq_array.argtypes = [C.c_void_p, C.c_int]
+        L.lins_seq_ints.restype = C.POINTER(C.c_int32)
+        L.lins_seq_ints.argtypes = [C.c_void_p, C.c_int]
+        _SEQ = L
+    return _SEQ
+
+
+def run_sequence(config="config3", seed=1, n_scans=12, device=0, **overrides):
+    """Drive fusion::StateEstimator (GPU hot path) over a synthetic sequence.  Returns the recorded performIESKF
+    units as a Batch plus the shim's outputs."""
+    L = seq_lib()
+    kw = dict(CONFIGS[config])
+    kw.update(overrides)
+    cfg = SynthCfg(**kw)
+    h = L.lins_seq_run(C.byref(cfg), seed, n_scans, device)
+    try:
+        n, ns = L.lins_seq_num_units(h), L.lins_seq_num_scans(h)
+        d = LinsBatchDesc()
+        L.lins_seq_desc(h, C.byref(d))
+        clouds, offsets = {}, {}
+        for k in Batch.FIELDS:
+            off = _copy(getattr(d, k + "_off"), n + 1, np.int32)
+            offsets[k] = off
+            clouds[k] = _copy(getattr(d, k), int(off[-1]), POINT_DTYPE)
+        arr = lambda which, cnt: np.ctypeslib.as_array(L.lins_seq_array(h, which), shape=(cnt,)).copy() if cnt else np.zeros(0)  # noqa: E731
+        ints = lambda which, cnt: np.ctypeslib.as_array(L.lins_seq_ints(h, which), shape=(cnt,)).copy() if cnt else np.zeros(0, np.int32)  # noqa: E731
+        units = Batch(clouds, offsets, _copy(d.state_in, n * 19, np.float64), _copy(d.cov_in, n * 324, np.float64), arr(1, n * 7)) if n else None
+        return dict(units=units, state_out=arr(0, n * 19).reshape(-1, 19), iters=ints(0, n), flags=ints(1, n), scan_index=ints(2, n),
+                    status=ints(3, ns), global_est=arr(2, ns * 7).reshape(-1, 7), global_true=arr(3, ns * 7).reshape(-1, 7))
+    finally:
+        L.lins_seq_destroy(h)

@@ -357,3 +357,24 @@ def test_full_size_properties(gpu, ob, synth):
     idx = list(range(0, 256, 16))
     so, co, ro, _, _ = ob.ieskf_batch(prm, b.subset(idx), threads=4)
     assert np.array_equal(r1["iters"][idx], ro["iters"]) and np.abs(s1[idx] - so).max() <= STATE_TOL
+
+
+def test_state_estimator_shim_sequence(gpu, ob, synth):
+    """Rows B / F3: the C++ mirror of fusion::StateEstimator (csrc/host/state_estimator.hpp) driven like LinsFusion
+    drives the reference (Estimator.cpp:204-252) over a synthetic drive.  Scan 1 initialises, scan 2 runs the ICP
+    initialiser, every later scan runs performIESKF on the device; each recorded update is replayed through the
+    oracle, and the relative motion must track the truth."""
+    out = synth.run_sequence("config3", seed=3, n_scans=12)
+    assert list(out["status"][:2]) == [1, 3] and (out["status"][2:] == 3).all()  # FIRST_SCAN, then RUNNING
+    units = out["units"]
+    assert units is not None and units.n == 10
+    prm = ob.LinsParams.shipped()
+    so, co, ro, _, _ = ob.ieskf_batch(prm, units, threads=2)
+    assert np.array_equal(out["iters"], ro["iters"]) and np.array_equal(out["flags"], ro["flags"].astype(np.int32))
+    ok = (out["flags"] & 2) == 0
+    assert ok.all()
+    assert np.abs(out["state_out"][ok] - so[ok]).max() <= STATE_TOL
+    # the estimate tracks the true per-scan motion (estimator accuracy on this synthetic world is ~1-2 cm)
+    terr = np.abs(out["state_out"][:, :3] - units.truth[:, :3])
+    assert terr.max() < 0.06, terr.max()
+    assert max(_rot_err(a, b) for a, b in zip(out["state_out"][:, 6:10], units.truth[:, 3:])) < 5e-3
