@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
   }
   __syncthreads();
 
+  const long long t_cta0 = clock64();
   PassBuffers pb;
   pb.qpt = qpt; pb.sel = selbuf; pb.qa = qabuf; pb.qw = qwbuf; pb.qref = qrefbuf; pb.qref2 = qref2buf; pb.qccr = qccrbuf; pb.key = key; pb.pos = posbuf; pb.azS = nullptr; pb.azC = nullptr;
 
@@ -70,7 +71,14 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
     if (tid == 0) { sm.scan = atomicAdd(bv.work_counter, 1); sm.tlast = clock64(); }
     __syncthreads();
     const int scan = sm.scan;
-    if (scan >= bv.n_scans) break;
+    if (scan >= bv.n_scans) {
+      if (bv.timers && tid == 0) {  // busy time of this CTA: sum and max over CTAs give the tail imbalance
+        const unsigned long long busy = (unsigned long long)(clock64() - t_cta0);
+        atomicAdd((unsigned long long*)&bv.timers[26], busy);
+        atomicMax((unsigned long long*)&bv.timers[27], busy);
+      }
+      break;
+    }
 
     // ---- prior -> shared ---------------------------------------------------------------------------------
     if (tid < 20) { double v = tid < 19 ? bv.state_in[(size_t)scan * 20 + tid] : 0.0; sm.prior[tid] = v; sm.lin[tid] = v; }
@@ -120,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
 
     // ---- the iterated update (StateEstimator.hpp:475-581) ---------------------------------------------------
     for (int iter = 0; iter < kp.num_iter; ++iter) {
+      const long long t_it0 = (bv.timers && tid == 0) ? clock64() : 0;
       if (tid == 0) compute_iter_consts(sm);
       __syncthreads();
       LINS_TICK(1);
@@ -127,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
       build_A6(sm);
       if (tid == 128) box_minus(sm);
       __syncthreads();
+      LINS_TICK(23);
       if (warp == 0) {
         if (lane < 6) {  // y = b6 + A6 d_c on the 6 structural rows
           double y = sm.y6[lane];
@@ -171,6 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
       }
       __syncthreads();
       LINS_TICK(8);
+      if (bv.timers && tid == 0 && iter == 0) atomicAdd((unsigned long long*)&bv.timers[24], (unsigned long long)(clock64() - t_it0));
       iters = iter + 1;
       if (sm.flags[3]) break;
     }
