@@ -107,20 +107,32 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
       __syncthreads();
       const float gate = sqrtf(nearf);
       for (int i = warp; i < nq; i += kWarps) {  // P2
-        const int w1 = pb.qw[i].x;
+        int w1 = pb.qw[i].x;
         if (w1 < -1) continue;  // closest point certified
         unsigned long long k1 = kKeyMax;
         unsigned second = 0xffffffffu;
         int p1 = -1;
         const bool surf = i < nsT;
-        if (w1 >= 0) k1 = az_scan_nn(surf ? ixS : ixC, pb.sel[i], w1, p1, second);
+        const AzIndex& ix = surf ? ixS : ixC;
+        const float4 s = pb.sel[i];
+        float4 qa = pb.qa[i];
+        if (w1 >= 0) {
+          const int wp = az_probe_window(ix, qa, w1);
+          if (wp >= 0) {  // wide window (no usable previous answer): probe first, then search inside the implied window
+            az_scan_nn(ix, s, wp, p1, second);
+            if (p1 >= 0) {
+              w1 = az_nn_window(ix, az_seed_bound(ix, s, p1, nearf), qa);
+              if (lane == 0) pb.qa[i] = qa;
+            }
+          }
+          k1 = az_scan_nn(ix, s, w1, p1, second);
+        }
         if (lane == 0) {
           const float d1 = __uint_as_float((unsigned)(k1 >> 32));
           const bool acc1 = k1 != kKeyMax && p1 >= 0 && (double)d1 < kp.nearest_sq;
-          const float4 s = pb.sel[i];
-          pb.qref[i] = make_float4(s.x, s.y, s.z, w1 >= 0 ? search_slack((unsigned)(k1 >> 32), second, pb.qa[i].w, gate, acc1) : -1.f);
+          pb.qref[i] = make_float4(s.x, s.y, s.z, w1 >= 0 ? search_slack((unsigned)(k1 >> 32), second, qa.w, gate, acc1) : -1.f);
           pb.pos[3 * i] = acc1 ? p1 : -1;
-          pb.qccr[i] = acc1 ? ((slot_ring((surf ? ixS : ixC).pts[p1].w) << 24) | (int)(unsigned)(k1 & 0xffffffffu)) : -1;
+          pb.qccr[i] = acc1 ? ((slot_ring(ix.pts[p1].w) << 24) | (int)(unsigned)(k1 & 0xffffffffu)) : -1;
         }
       }
       __syncthreads();
@@ -153,14 +165,34 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         if (w.x < 0) continue;  // certified (-2) or no closest point (-1)
         const bool surf = i < nsT;
         const int gq = q0 + i;
-        const float2 B = reinterpret_cast<const float2*>(pb.key)[i];
-        int i2, i3, p2, p3;
+        float2 B = reinterpret_cast<const float2*>(pb.key)[i];
+        int i2, i3, p2, p3, w2 = w.y, w3 = w.z;
         float slack;
-        if (surf) az_scan_walk<true>(ixS, pb.sel[i], w.w, w.y, w.z, fwdS, nearf, B.x, B.y, i2, i3, p2, p3, slack);
-        else az_scan_walk<false>(ixC, pb.sel[i], w.w, w.y, w.z, fwdC, nearf, B.x, B.y, i2, i3, p2, p3, slack);
+        const float4 s = pb.sel[i];
+        {  // wide windows (no usable previous answer): probe a small window first and re-window from what it finds
+          const float4 qa = pb.qa[i];
+          const int wide = max(w2 & 0xffff, surf ? (w3 & 0xffff) : 0);
+          const int wp = az_probe_window(surf ? ixS : ixC, qa, wide);
+          if (wp >= 0) {
+            const int c = w.w & 0x00ffffff, cr = (int)((unsigned)w.w >> 24);
+            const int sd2 = seeded ? pb.pos[3 * i + 1] : -1, sd3 = seeded ? pb.pos[3 * i + 2] : -1;
+            float b2, b3;
+            int pw2, pw3;
+            if (surf) {
+              az_prepare_walk<true>(ixS, s, qa, c, cr, -1, -1, fwdS, kProbeSq, pw2, pw3, b2, b3);
+              az_scan_walk<true>(ixS, s, w.w, pw2, pw3, fwdS, nearf, b2, b3, i2, i3, p2, p3, slack);
+              az_prepare_walk<true>(ixS, s, qa, c, cr, sd2, sd3, fwdS, nearf, w2, w3, B.x, B.y, p2, p3);
+            } else {
+              az_prepare_walk<false>(ixC, s, qa, c, cr, -1, -1, fwdC, kProbeSq, pw2, pw3, b2, b3);
+              az_scan_walk<false>(ixC, s, w.w, pw2, pw3, fwdC, nearf, b2, b3, i2, i3, p2, p3, slack);
+              az_prepare_walk<false>(ixC, s, qa, c, cr, sd2, sd3, fwdC, nearf, w2, w3, B.x, B.y, p2, p3);
+            }
+          }
+        }
+        if (surf) az_scan_walk<true>(ixS, s, w.w, w2, w3, fwdS, nearf, B.x, B.y, i2, i3, p2, p3, slack);
+        else az_scan_walk<false>(ixC, s, w.w, w2, w3, fwdC, nearf, B.x, B.y, i2, i3, p2, p3, slack);
         if (lane == 0) {
           pb.pos[3 * i + 1] = p2; pb.pos[3 * i + 2] = p3;
-          const float4 s = pb.sel[i];
           pb.qref2[i] = make_float4(s.x, s.y, s.z, slack);
           const int i1 = w.w & 0x00ffffff;
           if (surf) { int* o = bv.ind_s + 3 * (size_t)(qs0 + gq); o[0] = i1; o[1] = i2; o[2] = i3; }
@@ -255,8 +287,10 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
       }
     }
     LINS_TICK(6);
-    block_reduce_acc(sm, acc, cntS, cntC);
+    // the fused update finishes the last tile's sum inside warp 0's serial tail (one barrier less)
+    block_reduce_acc(sm, acc, cntS, cntC, !(MODE == MODE_IESKF && q0 + bv.qtile >= ntot));
   }
+  if (ntot == 0) __syncthreads();  // no tile ran: still order the zeroed sums before the caller reads them
   LINS_TICK(7);
 }
 

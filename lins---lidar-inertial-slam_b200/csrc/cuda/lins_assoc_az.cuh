@@ -152,22 +152,38 @@ __device__ __forceinline__ void az_polar(const float4 s, float4& qa) {
   qa.x = atan2f(s.y, s.x);
   qa.y = sqrtf(__fadd_rn(__fmul_rn(s.x, s.x), __fmul_rn(s.y, s.y)));
 }
-__device__ __forceinline__ int az_prepare_nn(const AzIndex& ix, const float4 s, float nearf, int seed_slot, float4& qa) {
-  qa = make_float4(0.f, 0.f, -1.f, 0.f);
-  if (!(s.x == s.x && s.y == s.y && s.z == s.z) || ix.T <= 0) return -1;
-  az_polar(s, qa);
-  const float aq = qa.x, rho = qa.y;
-  float U1 = nearf;  // nothing beyond the gate can be accepted (StateEstimator.hpp:851)
+// window of the closest-point search given an upper bound U1 on its answer (the gate, or the distance to any real
+// target); qa.w <- distance bound of everything outside the window
+__device__ __forceinline__ int az_nn_window(const AzIndex& ix, float U1, float4& qa) {
+  const float Uw = widen(U1);
+  int blo, nbins;
+  az_window(ix.nb, qa.x, az_halfwidth(Uw, qa.y), blo, nbins);
+  qa.w = nbins >= ix.nb ? 3.0e38f : sqrtf(Uw);
+  return pack_window(blo, nbins);
+}
+__device__ __forceinline__ float az_seed_bound(const AzIndex& ix, const float4 s, int seed_slot, float U1) {
   if (seed_slot >= 0 && seed_slot < ix.T) {
     const float4 t = ix.pts[seed_slot];
     const float d = sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z);
     if (d < U1) U1 = d;
   }
-  const float Uw = widen(U1);
+  return U1;
+}
+__device__ __forceinline__ int az_prepare_nn(const AzIndex& ix, const float4 s, float nearf, int seed_slot, float4& qa) {
+  qa = make_float4(0.f, 0.f, -1.f, 0.f);
+  if (!(s.x == s.x && s.y == s.y && s.z == s.z) || ix.T <= 0) return -1;
+  az_polar(s, qa);
+  // nothing beyond the gate can be accepted (StateEstimator.hpp:851)
+  return az_nn_window(ix, az_seed_bound(ix, s, seed_slot, nearf), qa);
+}
+// Probe radius: a search whose window (built from the gate, i.e. without a usable previous answer) is much wider
+// than the window of this radius first scans the small window; the best candidate found there is a real target,
+// so its distance is a valid upper bound and the exact search runs inside the (much smaller) window it implies.
+constexpr float kProbeSq = 0.25f;  // (0.5 m)^2
+__device__ __forceinline__ int az_probe_window(const AzIndex& ix, const float4 qa, int full_window) {
   int blo, nbins;
-  az_window(ix.nb, aq, az_halfwidth(Uw, rho), blo, nbins);
-  qa.w = nbins >= ix.nb ? 3.0e38f : sqrtf(Uw);  // everything outside the window is farther than this
-  return pack_window(blo, nbins);
+  az_window(ix.nb, qa.x, az_halfwidth(kProbeSq, qa.y), blo, nbins);
+  return (full_window & 0xffff) > 2 * nbins + 4 ? pack_window(blo, nbins) : -1;
 }
 
 // ---- phase P2 (one WARP per query): exact 1-NN over all rings inside the window ---------------------------------
@@ -234,21 +250,28 @@ __device__ __forceinline__ unsigned long long az_scan_nn(const AzIndex& ix, cons
 
 // ---- phase P3 (one THREAD per query): bound + window the walks of a query whose closest point is (c, cr) -------
 // w2 / w3 = windows of the Ind2 / Ind3 searches, B2 / B3 = distance bound of everything outside them
+// bound from a candidate slot while it is an admissible candidate of THIS search (CLS2: the Ind2 search)
+template <bool SURF, bool CLS2>
+__device__ __forceinline__ float walk_seed_bound(const AzIndex& ix, const float4 s, int seed, int c, int cr, int fwdBound, float U) {
+  if (seed >= 0 && seed < ix.T) {
+    const float4 t = ix.pts[seed];
+    const int j = slot_index(t.w), r = slot_ring(t.w);
+    const bool ring_ok = (SURF && CLS2) ? (r == cr) : (r != cr && r >= cr - 2 && r <= cr + 2);
+    if (ring_ok && j != c && (j < c || j < fwdBound)) { const float d = sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z); if (d < U) U = d; }
+  }
+  return U;
+}
+// Uinit = NEAREST_FEATURE_SEARCH_SQ_DIST for a real search (nothing beyond the gate is accepted), kProbeSq for a probe
 template <bool SURF>
 __device__ __forceinline__ void az_prepare_walk(const AzIndex& ix, const float4 s, const float4 qa, int c, int cr, int seed2,
-                                                int seed3, int fwdBound, float nearf, int& w2, int& w3, float& B2, float& B3) {
-  // bounds from the previous answers while they are still admissible candidates of THIS search
-  float U2 = nearf, U3 = nearf;
-  if (seed2 >= 0 && seed2 < ix.T) {
-    const float4 t = ix.pts[seed2];
-    const int j = slot_index(t.w), r = slot_ring(t.w);
-    const bool ring_ok = SURF ? (r == cr) : (r != cr && r >= cr - 2 && r <= cr + 2);
-    if (ring_ok && j != c && (j < c || j < fwdBound)) { const float d = sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z); if (d < U2) U2 = d; }
-  }
-  if (SURF && seed3 >= 0 && seed3 < ix.T) {
-    const float4 t = ix.pts[seed3];
-    const int j = slot_index(t.w), r = slot_ring(t.w);
-    if (r != cr && r >= cr - 2 && r <= cr + 2 && (j < c || j < fwdBound)) { const float d = sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z); if (d < U3) U3 = d; }
+                                                int seed3, int fwdBound, float Uinit, int& w2, int& w3, float& B2, float& B3,
+                                                int seed2b = -1, int seed3b = -1) {
+  // bounds from the previous answers (and / or a probe's answers)
+  float U2 = walk_seed_bound<SURF, true>(ix, s, seed2, c, cr, fwdBound, Uinit), U3 = Uinit;
+  U2 = walk_seed_bound<SURF, true>(ix, s, seed2b, c, cr, fwdBound, U2);
+  if (SURF) {
+    U3 = walk_seed_bound<SURF, false>(ix, s, seed3, c, cr, fwdBound, U3);
+    U3 = walk_seed_bound<SURF, false>(ix, s, seed3b, c, cr, fwdBound, U3);
   }
   int blo, nbins;
   const float Uw2 = widen(U2);

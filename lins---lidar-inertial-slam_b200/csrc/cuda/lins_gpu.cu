@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
     LINS_TICK(0);
 
     if (MODE == MODE_ASSOC || MODE == MODE_ICP_REDUCE) {
-      if (tid == 0) compute_iter_consts(sm);
+      if (warp == 0) iter_consts_warp0(sm);
       __syncthreads();
       association_pass<MODE>(sm, bv, kp, scan, kp.iter0, pb, true);
       if (bv.accum) {
@@ -127,17 +127,20 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
     }
 
     // ---- the iterated update (StateEstimator.hpp:475-581) ---------------------------------------------------
+    // One block barrier separates the data-parallel part of an iteration (association_pass) from its serial tail,
+    // which warp 0 runs alone: finish the reduction, 6x6 gain system, update, convergence logic, and the constants of
+    // the NEXT iteration (so the loop has no other barrier of its own).
+    const int nq_scan = (bv.qs_off[scan + 1] - bv.qs_off[scan]) + (bv.qc_off[scan + 1] - bv.qc_off[scan]);
+    if (warp == 0) iter_consts_warp0(sm);
+    __syncthreads();
     for (int iter = 0; iter < kp.num_iter; ++iter) {
       const long long t_it0 = (bv.timers && tid == 0) ? clock64() : 0;
-      if (tid == 0) compute_iter_consts(sm);
-      __syncthreads();
       LINS_TICK(1);
       association_pass<MODE>(sm, bv, kp, scan, iter, pb, iter == 0);
-      build_A6(sm);
-      if (tid == 128) box_minus(sm);
-      __syncthreads();
-      LINS_TICK(23);
       if (warp == 0) {
+        if (nq_scan > 0) finish_acc_warp0(sm);  // (an empty scan has no partial sums: the update comes from the prior alone)
+        build_A6_warp0(sm);
+        LINS_TICK(18);
         if (lane < 6) {  // y = b6 + A6 d_c on the 6 structural rows
           double y = sm.y6[lane];
           for (int c = 0; c < 6; ++c) y += sm.A6[lane * 6 + c] * sm.dvec[col6(c)];
@@ -145,25 +148,26 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
         }
         form_M6(sm, sig2, lane, 32);
         __syncwarp();
-        const bool ok = warp_lu_solve<6>(sm.M6, sm.X6, 1);  // z = M^-1 (b6 + A6 d_c)
+        const bool ok = warp_lu_cols<6>(sm.M6, sm.X6, 1);  // z = M^-1 (b6 + A6 d_c)
         __syncwarp();
+        LINS_TICK(19);
+        double u = 0.0;
         if (lane < 18) {  // K (r + H d) = P[:,c] z
           double kx = 0;
           for (int c = 0; c < 6; ++c) kx += sm.P[lane * 18 + col6(c)] * sm.X6[c];
-          sm.upd[lane] = ok ? (-kx + sm.dvec[lane]) : __longlong_as_double(0x7ff8000000000000ll);
+          u = ok ? (-kx + sm.dvec[lane]) : __longlong_as_double(0x7ff8000000000000ll);
         }
+        const bool hasNaN = __ballot_sync(0xffffffffu, u != u) != 0u;  // :553-558
+        if (u != u) u = 0.0;
+        if (lane < 18) sm.upd[lane] = u;
         __syncwarp();
+        double nrm = 0.0;  // lane 0: ||update||^2 (sequential order), lane 1: ||residual||^2
+        if (lane == 0) for (int a = 0; a < 18; ++a) nrm += sm.upd[a] * sm.upd[a];
+        if (lane == 1) nrm = sm.acc[27];
+        nrm = sqrt(nrm);
+        const double un = __shfl_sync(0xffffffffu, nrm, 0), rnorm = __shfl_sync(0xffffffffu, nrm, 1);
+        LINS_TICK(21);
         if (lane == 0) {
-          bool hasNaN = false;
-          for (int a = 0; a < 18; ++a) {
-            double u = sm.upd[a];
-            if (u != u) { u = 0.0; hasNaN = true; }  // :553-558
-            sm.upd[a] = u;
-          }
-          double un = 0;
-          for (int a = 0; a < 18; ++a) un += sm.upd[a] * sm.upd[a];
-          un = sqrt(un);
-          const double rnorm = sqrt(sm.acc[27]);
           if (rep) {
             rep->m_surf[iter] = sm.cnt[0]; rep->m_corner[iter] = sm.cnt[1];
             rep->residual_norm[iter] = rnorm; rep->update_norm[iter] = un;
@@ -178,6 +182,10 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
             sm.residualNorm = rnorm;
           }
         }
+        __syncwarp();
+        LINS_TICK(23);
+        if (!sm.flags[3] && iter + 1 < kp.num_iter) iter_consts_warp0(sm);
+        LINS_TICK(25);
       }
       __syncthreads();
       LINS_TICK(8);
@@ -198,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
       }
       __syncthreads();
       if (warp == 0) {
-        const bool ok = warp_lu_solve<6>(sm.M6, sm.X6, 12);
+        const bool ok = warp_lu_cols<6>(sm.M6, sm.X6, 12);
         if (!ok) for (int e = lane; e < 72; e += 32) sm.X6[e] = __longlong_as_double(0x7ff8000000000000ll);
       }
       __syncthreads();

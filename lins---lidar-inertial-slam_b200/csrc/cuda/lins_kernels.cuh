@@ -375,7 +375,9 @@ __device__ __forceinline__ void accumulate_row_icp(const float4 kp, const float4
 }
 
 // fixed-tree block reduction of the per-thread accumulators into sm.acc / sm.cnt
-__device__ void block_reduce_acc(Smem& sm, double* acc, int cs, int cc) {
+// finish = false: stop after the per-warp partial sums are in shared memory (one barrier); the caller's warp 0
+// adds them with finish_acc_warp0.
+__device__ void block_reduce_acc(Smem& sm, double* acc, int cs, int cc, bool finish = true) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int k = 0; k < kNAcc; ++k) {
@@ -388,6 +390,7 @@ __device__ void block_reduce_acc(Smem& sm, double* acc, int cs, int cc) {
   for (int m = 16; m > 0; m >>= 1) { cs += __shfl_xor_sync(0xffffffffu, cs, m); cc += __shfl_xor_sync(0xffffffffu, cc, m); }
   if (lane == 0) { sm.wcnt[warp][0] = cs; sm.wcnt[warp][1] = cc; }
   __syncthreads();
+  if (!finish) return;
   if (threadIdx.x < kNAcc) {  // accumulates: callers zero sm.acc / sm.cnt at the start of a pass
     double v = sm.acc[threadIdx.x];
     for (int w = 0; w < kWarps; ++w) v += sm.wacc[w][threadIdx.x];
@@ -527,6 +530,166 @@ __device__ void box_plus(Smem& sm) {
   q4 dq = axis2Quat(mk3(u[6], u[7], u[8]));
   q4 r = qnormalized(qmul(q, dq));
   l[6] = r.x; l[7] = r.y; l[8] = r.z; l[9] = r.w;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// The serial tail of an iteration, executed by warp 0 alone between two block barriers.  Everything below is
+// written so that the 32 lanes work on different entries of the same small formula in lockstep.
+
+// N x N LU with partial pivoting, one COLUMN per lane held in registers: lanes [0, N) own the columns of S
+// (row-major in shared memory), lanes [N, N + nrhs) the right-hand sides B (N x nrhs row-major, overwritten by
+// the solution).  Same pivot rule (first maximum of |column| from the diagonal down; a NaN on the diagonal
+// poisons the step) and the same multiply / subtract sequence per entry as warp_lu_solve, at a third of its
+// latency: no shared-memory round trips, one division per step.  nrhs <= 32 - N.
+template <int N>
+__device__ bool warp_lu_cols(const double* S, double* B, int nrhs) {
+  const int lane = threadIdx.x & 31;
+  const bool is_rhs = lane >= N && lane < N + nrhs;
+  double c[N];
+#pragma unroll
+  for (int r = 0; r < N; ++r) c[r] = lane < N ? S[r * N + lane] : (is_rhs ? B[r * nrhs + (lane - N)] : 0.0);
+  double dinv = 0.0;  // lane k keeps 1 / U[k][k]
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    int piv = k;
+    double best = fabs(c[k]);
+#pragma unroll
+    for (int r = k + 1; r < N; ++r) {
+      const double v = fabs(c[r]);
+      if (v > best) { best = v; piv = r; }
+    }
+    piv = __shfl_sync(0xffffffffu, piv, k);
+    best = __shfl_sync(0xffffffffu, best, k);
+    if (!(best > 0.0)) { ok = false; break; }  // singular or NaN pivot (uniform: broadcast value)
+#pragma unroll
+    for (int r = k + 1; r < N; ++r)
+      if (piv == r) { const double t = c[k]; c[k] = c[r]; c[r] = t; }
+    const double inv = 1.0 / c[k];  // meaningful in lane k
+    if (lane == k) dinv = inv;
+#pragma unroll
+    for (int r = k + 1; r < N; ++r) {
+      const double f = __shfl_sync(0xffffffffu, c[r] * inv, k);
+      if (f != 0.0 && lane > k) c[r] -= f * c[k];
+    }
+  }
+  if (!ok) return false;
+#pragma unroll
+  for (int k = N - 1; k >= 0; --k) {
+    double sacc = c[k];
+#pragma unroll
+    for (int m = k + 1; m < N; ++m) {
+      const double u = __shfl_sync(0xffffffffu, c[k], m);  // U[k][m] lives in lane m
+      sacc -= u * c[m];
+    }
+    const double inv = __shfl_sync(0xffffffffu, dinv, k);
+    if (is_rhs) c[k] = sacc * inv;
+  }
+  if (is_rhs) {
+#pragma unroll
+    for (int r = 0; r < N; ++r) B[r * nrhs + (lane - N)] = c[r];
+  }
+  return true;
+}
+
+// sm.acc / sm.cnt += the per-warp partial sums of the last tile (block_reduce_acc with finish = false)
+__device__ __forceinline__ void finish_acc_warp0(Smem& sm) {
+  const int lane = threadIdx.x & 31;
+  if (lane < kNAcc) {
+    double v = sm.acc[lane];
+    for (int w = 0; w < kWarps; ++w) v += sm.wacc[w][lane];
+    sm.acc[lane] = v;
+  } else if (lane < kNAcc + 2) {
+    const int k = lane - kNAcc;
+    int a = sm.cnt[k];
+    for (int w = 0; w < kWarps; ++w) a += sm.wcnt[w][k];
+    sm.cnt[k] = a;
+  }
+  __syncwarp();
+}
+
+// A6 = T Ag T^T and y6 = T b with T = blockdiag(I3, Rinv^T), entry by entry with the structural zeros of T
+// skipped (adding those zero products would not change a finite result).  Two lockstep rounds: the 27 entries
+// that need arithmetic + 5 copies, then 4 copies + y6.
+__device__ __forceinline__ void build_A6_warp0(Smem& sm) {
+  const int lane = threadIdx.x & 31;
+  auto Ag = [&](int i, int j) -> double {
+    if (i > j) { const int tmp = i; i = j; j = tmp; }
+    return sm.acc[i * 6 - (i * (i - 1)) / 2 + (j - i)];
+  };
+  auto entry = [&](int a, int c) -> double {
+    if (a < 3 && c < 3) return Ag(a, c);
+    if (a < 3) {  // Ag12 Rinv
+      double u = 0;
+      for (int j = 0; j < 3; ++j) u += Ag(a, 3 + j) * sm.Rinv[j * 3 + (c - 3)];
+      return u;
+    }
+    if (c < 3) {  // Rinv^T Ag21
+      double v = 0;
+      for (int i = 0; i < 3; ++i) v += sm.Rinv[i * 3 + (a - 3)] * Ag(3 + i, c);
+      return v;
+    }
+    double v = 0;  // Rinv^T Ag22 Rinv
+    for (int i = 0; i < 3; ++i) {
+      double u = 0;
+      for (int j = 0; j < 3; ++j) u += Ag(3 + i, 3 + j) * sm.Rinv[j * 3 + (c - 3)];
+      v += sm.Rinv[i * 3 + (a - 3)] * u;
+    }
+    return v;
+  };
+  // entry order: [3..5]x[3..5] (9), [0..2]x[3..5] (9), [3..5]x[0..2] (9), [0..2]x[0..2] (9)
+  auto coords = [&](int e, int& a, int& c) {
+    const int blk = e / 9, w = e % 9;
+    a = w / 3 + ((blk == 0 || blk == 2) ? 3 : 0);
+    c = w % 3 + ((blk == 0 || blk == 1) ? 3 : 0);
+  };
+  {
+    int a, c;
+    coords(lane, a, c);
+    sm.A6[a * 6 + c] = entry(a, c);
+  }
+  if (lane < 4) {
+    int a, c;
+    coords(32 + lane, a, c);
+    sm.A6[a * 6 + c] = entry(a, c);
+  } else if (lane < 10) {
+    const int a = lane - 4;
+    double v = 0;
+    if (a < 3) v = sm.acc[21 + a];
+    else for (int i = 0; i < 3; ++i) v += sm.Rinv[i * 3 + (a - 3)] * sm.acc[24 + i];
+    sm.y6[a] = v;  // b_h (A6 d_c is added by the caller)
+  }
+  __syncwarp();
+}
+
+// Start-of-iteration constants and filterState (-) linState in one lockstep pass: lane 0 derives phi, R, Rinv
+// from the iterate, lane 1 the attitude part of boxMinus — both are Quat2axis of a quaternion, so the expensive
+// part runs once for the two lanes.  (compute_iter_consts + box_minus, KalmanFilter.hpp:84-94.)
+__device__ __forceinline__ void iter_consts_warp0(Smem& sm) {
+  const int lane = threadIdx.x & 31;
+  const double* f = sm.prior; const double* l = sm.lin;
+  if (lane >= 2 && lane < 17) {  // the 15 vector-space components of boxMinus
+    const int e = lane - 2, blk = e / 3, i = e % 3;
+    const int so = blk == 0 ? 0 : blk == 1 ? 3 : 10 + 3 * (blk - 2);   // state offsets 0,3,10,13,16
+    const int eo = blk == 0 ? 0 : blk == 1 ? 3 : 9 + 3 * (blk - 2);    // error-state offsets 0,3,9,12,15
+    sm.dvec[eo + i] = f[so + i] - l[so + i];
+  }
+  if (lane < 2) {
+    q4 ql; ql.x = l[6]; ql.y = l[7]; ql.z = l[8]; ql.w = l[9];
+    q4 qf; qf.x = f[6]; qf.y = f[7]; qf.z = f[8]; qf.w = f[9];
+    const q4 qd = qmul(qinverse(ql), qf);
+    const q4 qin = lane == 0 ? ql : qd;
+    const d3 ax = Quat2axis(qin);
+    if (lane == 1) { sm.dvec[6] = ax.x; sm.dvec[7] = ax.y; sm.dvec[8] = ax.z; }
+    else {
+      sm.phi[0] = ax.x; sm.phi[1] = ax.y; sm.phi[2] = ax.z;
+      const m3 R = qtoR(ql);
+      const m3 Ri = Rinvleft(mk3(-ax.x, -ax.y, -ax.z));
+      for (int i = 0; i < 9; ++i) { sm.R[i] = R.m[i]; sm.Rinv[i] = Ri.m[i]; }
+    }
+  }
+  __syncwarp();
 }
 
 }  // namespace lins_dev

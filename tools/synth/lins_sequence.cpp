@@ -5,6 +5,8 @@
 // image projection).  The estimator is the C++ shim fusion::StateEstimator whose hot seams run on the GPU through
 // the C-ABI, so this file links against liblins_gpu.so.  Every performIESKF call's inputs / outputs are recorded
 // so that tests can replay them through the CPU oracle.  Never includes anything from oracle/.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -65,8 +67,10 @@ void* lins_seq_run(const lins_synth_cfg* cfg, uint64_t seed, int n_scans, int de
   StateEstimator est(ep, device);
   ImageProjection ip(lm);
 
+  const bool verbose = std::getenv("LINS_SEQ_VERBOSE") != nullptr;
   double t = 0.0;
   for (int k = 0; k < n_scans; ++k) {
+    if (verbose) std::fprintf(stderr, "[lins_seq] simulating scan %d\n", k);
     // ---- simulate one sweep: poses at the 40 IMU instants, IMU samples, 1800 firings ---------------------------
     std::vector<Pose> poses(nimu + 1);
     std::vector<V3D> accs(nimu + 1), gyrs(nimu + 1);
@@ -119,6 +123,7 @@ void* lins_seq_run(const lins_synth_cfg* cfg, uint64_t seed, int n_scans, int de
     est.last_report_.iters = 0;
     est.processPCL(t, lins::sensor_utils::Imu(t, accs[nimu], gyrs[nimu]), ip.segmentedCloud, ip.segMsg, ip.outlierCloud);
     rec->status.push_back((int)est.status_);
+    if (verbose) std::fprintf(stderr, "[lins_seq] scan %d: status %d, IESKF iterations %d, %zu segmented points\n", k, (int)est.status_, (int)est.last_report_.iters, ip.segmentedCloud.size());
     if (will_run && est.last_report_.iters > 0) {
       // processScan swapped the scans: scan_last_ now IS the scan whose features were the queries
       append_cloud(rec->surfFlat, rec->offSF, est.scan_last_->surfPointsFlat_);
