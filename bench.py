@@ -104,6 +104,16 @@ def algorithmic_bytes(batch, iters):
     return int(per_scan.sum())
 
 
+def profiled_traffic(key):
+    """DRAM bytes per launch of the named kernel from the committed `ncu --set full` capture of this same command
+    (profiles/traffic.json, written by tools/ncu_summary.py); None when no capture is recorded."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)[key]["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def jacobian_bytes(batch):
     """76 B per surf query + 56 B per corner query + 384 B per scan."""
     ns = int(batch.offsets["surf_flat"][-1]); nc = int(batch.offsets["corner_sharp"][-1])
@@ -278,7 +288,7 @@ def main():
     kms = float(np.mean(kernel_ms))
     achieved = alg / (kms * 1e-3) / 1e9
     roofline = {"kernel": "lins_ieskf_kernel<MODE_IESKF> (fused de-skew + 1-NN + ring walks + residual/Jacobian fold + 18x18 solve, all iterations)",
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic("fused"),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": kms,
                 "note": "latency/issue bound by design: per scan ~90 KB of compulsory bytes feed ~10^7 f32 distance evaluations served from L1/L2; see DESIGN.md"}
     # Jacobian kernel: tile the resident batch past L2 and time the split kernel alone
@@ -297,7 +307,7 @@ def main():
     jms = ja.elapsed_time(jb_) / reps
     jbytes = jacobian_bytes(jb)
     roofline_j = {"kernel": "lins_jacobian_kernel (SURVEY.md §8(d) unit U1, given correspondence IDs)", "bound": "hbm", "achieved": jbytes / (jms * 1e-3) / 1e9,
-                  "peak": peak, "unit": "GB/s", "frac": jbytes / (jms * 1e-3) / 1e9 / peak, "traffic": None, "scans": jb.n, "avg_launch_ms": jms,
+                  "peak": peak, "unit": "GB/s", "frac": jbytes / (jms * 1e-3) / 1e9 / peak, "traffic": profiled_traffic("jacobian"), "scans": jb.n, "avg_launch_ms": jms,
                   "algorithmic_bytes_per_launch": jbytes, "working_set_mb": (16 * sum(int(jb.offsets[k][-1]) for k in jb.FIELDS)) / 1e6}
     jctx.close()
 

@@ -36,11 +36,13 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 def build(force=False, verbose=False):
     """Compile csrc/cuda/lins_gpu.cu -> liblins_gpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CUDA_DIR, f) for f in ("lins_gpu.cu", "lins_kernels.cuh", "lins_device_math.cuh")]
-    srcs.append(os.path.join(_ROOT, "include", "lins_gpu.h"))
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+    main = os.path.join(CUDA_DIR, "lins_gpu.cu")
+    deps = [main, os.path.join(_ROOT, "include", "lins_gpu.h")]
+    for d in (CUDA_DIR, os.path.join(os.path.dirname(CUDA_DIR), "host")):  # every header the translation unit includes
+        deps += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cuh", ".hpp", ".h"))]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in deps):
         return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, srcs[0]]
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, main]
     subprocess.check_call(cmd)
     return LIB_PATH
 

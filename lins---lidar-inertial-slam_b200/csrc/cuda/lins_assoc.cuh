@@ -21,6 +21,7 @@ struct PassBuffers {
   float4* qref;              // fast path: pointSel at the last closest-point search + the slack (m) of its answer
   float4* qref2;             // fast path: pointSel at the last walk search + the slack of Ind2 / Ind3
   int* qccr;                 // fast path: (ring << 24 | original index) of the closest point, -1 = none
+  int* wl;                   // fast path: work list of the queries that need a closest-point search / ring walks this pass
   const float4* azS;         // sorted copies (shared or global)
   const float4* azC;
 };
@@ -82,6 +83,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
       pb.sel[i] = transform_to_start(pb.qpt[i], sm, kp.scan_period);
       pb.key[i] = kKeyMax;
     }
+    if (threadIdx.x == kThreads - 1) { sm.wl_n[0] = 0; sm.wl_n[1] = 0; sm.wl_head[0] = 0; sm.wl_head[1] = 0; sm.dbg[0] = 0; sm.dbg[1] = 0; }
     __syncthreads();
     LINS_TICK(3);
     if (search && fast) {
@@ -103,12 +105,24 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         const int w1 = az_prepare_nn(surf ? ixS : ixC, s, nearf, seeded ? pb.pos[3 * i] : -1, qa);
         pb.qa[i] = qa;
         pb.qw[i] = make_int4(w1, 0, 0, 0);
+        pb.wl[atomicAdd(&sm.wl_n[0], 1)] = i;  // (list order does not matter: every query's result goes to its own slot)
+        if (bv.timers && w1 >= 0) atomicAdd(&sm.dbg[0], w1 & 0xffff);
       }
       __syncthreads();
+      if (bv.timers && threadIdx.x == 0) {
+        atomicAdd((unsigned long long*)&bv.timers[10], (unsigned long long)sm.wl_n[0]);
+        atomicAdd((unsigned long long*)&bv.timers[12], (unsigned long long)sm.dbg[0]);
+        if (first_pass_of_scan) atomicAdd((unsigned long long*)&bv.timers[14], (unsigned long long)sm.dbg[0]);
+      }
       const float gate = sqrtf(nearf);
-      for (int i = warp; i < nq; i += kWarps) {  // P2
+      // P2: warps pull queries from the work list (the per-query cost is heavy-tailed; a static split leaves warps idle)
+      for (;;) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&sm.wl_head[0], 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= sm.wl_n[0]) break;
+        const int i = pb.wl[k];
         int w1 = pb.qw[i].x;
-        if (w1 < -1) continue;  // closest point certified
         unsigned long long k1 = kKeyMax;
         unsigned second = 0xffffffffu;
         int p1 = -1;
@@ -158,11 +172,22 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         else az_prepare_walk<false>(ixC, pb.sel[i], pb.qa[i], c, cr, sd2, sd3, fwdC, nearf, w2, w3, B2, B3);
         pb.qw[i] = make_int4(1, w2, w3, ccr);
         reinterpret_cast<float2*>(pb.key)[i] = make_float2(B2, B3);
+        pb.wl[atomicAdd(&sm.wl_n[1], 1)] = i;
+        if (bv.timers) atomicAdd(&sm.dbg[1], (w2 & 0xffff) + 4 * (w3 & 0xffff));
       }
       __syncthreads();
-      for (int i = warp; i < nq; i += kWarps) {  // P4
+      if (bv.timers && threadIdx.x == 0) {
+        atomicAdd((unsigned long long*)&bv.timers[11], (unsigned long long)sm.wl_n[1]);
+        atomicAdd((unsigned long long*)&bv.timers[13], (unsigned long long)sm.dbg[1]);
+        if (first_pass_of_scan) atomicAdd((unsigned long long*)&bv.timers[15], (unsigned long long)sm.dbg[1]);
+      }
+      for (;;) {  // P4: same work-list scheme
+        int k = 0;
+        if (lane == 0) k = atomicAdd(&sm.wl_head[1], 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= sm.wl_n[1]) break;
+        const int i = pb.wl[k];
         const int4 w = pb.qw[i];
-        if (w.x < 0) continue;  // certified (-2) or no closest point (-1)
         const bool surf = i < nsT;
         const int gq = q0 + i;
         float2 B = reinterpret_cast<const float2*>(pb.key)[i];

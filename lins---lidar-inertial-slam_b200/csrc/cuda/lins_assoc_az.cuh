@@ -180,7 +180,9 @@ __device__ __forceinline__ int az_prepare_nn(const AzIndex& ix, const float4 s, 
 // than the window of this radius first scans the small window; the best candidate found there is a real target,
 // so its distance is a valid upper bound and the exact search runs inside the (much smaller) window it implies.
 constexpr float kProbeSq = 0.25f;  // (0.5 m)^2
+constexpr bool kUseProbe = false;  // measured slower on the VLP-16 workload (per-query cost is latency, not candidates)
 __device__ __forceinline__ int az_probe_window(const AzIndex& ix, const float4 qa, int full_window) {
+  if (!kUseProbe) return -1;
   int blo, nbins;
   az_window(ix.nb, qa.x, az_halfwidth(kProbeSq, qa.y), blo, nbins);
   return (full_window & 0xffff) > 2 * nbins + 4 ? pack_window(blo, nbins) : -1;
@@ -193,17 +195,28 @@ __device__ __forceinline__ void take(unsigned long long k, int p, unsigned long 
   if (k < best) { second = (unsigned)(best >> 32); best = k; bpos = p; }
   else { const unsigned d = (unsigned)(k >> 32); second = d < second ? d : second; }
 }
+// A candidate farther than the lane's current runner-up can change neither its best nor its runner-up (`second` is
+// never below the best's distance), so the common case costs the distance and one compare; four candidates per lane
+// are in flight per trip (the scan is latency / issue bound, not bandwidth bound).
 template <int LPR>
 __device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4 s, int p, int pe, unsigned long long& best,
                                                  unsigned& second, int& bpos) {
-  for (; p < pe; p += 2 * LPR) {
-    const int pb2 = p + LPR;
-    const float4 t0 = ix.pts[p];
-    const float4 t1 = ix.pts[pb2 < pe ? pb2 : p];
-    const unsigned long long k0 = pack_key(sqdist_f32(s.x, s.y, s.z, t0.x, t0.y, t0.z), (unsigned)slot_index(t0.w));
-    const unsigned long long k1 = pack_key(sqdist_f32(s.x, s.y, s.z, t1.x, t1.y, t1.z), (unsigned)slot_index(t1.w));
-    take(k0, p, best, second, bpos);
-    if (pb2 < pe) take(k1, pb2, best, second, bpos);
+  for (; p < pe; p += 4 * LPR) {
+    float4 t[4];
+    unsigned d[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int pu = p + u * LPR; t[u] = ix.pts[pu < pe ? pu : p]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      d[u] = __float_as_uint(sqdist_f32(s.x, s.y, s.z, t[u].x, t[u].y, t[u].z));
+      if (p + u * LPR >= pe) d[u] = 0xffffffffu;  // (0xffffffff is never <= a runner-up that a real candidate has set)
+    }
+    const unsigned dmin = min(min(d[0], d[1]), min(d[2], d[3]));
+    if (dmin <= second) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (p + u * LPR < pe && d[u] <= second) take(((unsigned long long)d[u] << 32) | (unsigned)slot_index(t[u].w), p + u * LPR, best, second, bpos);
+    }
   }
 }
 // warp arg-min that also yields the distance bits of the overall runner-up
@@ -297,12 +310,13 @@ __device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, 
   // keys are NOT gated here: the minimum over the candidates is needed even when it lies beyond the gate (to certify
   // "still nothing within the gate"); the gate is applied to the reduced winner, which is equivalent to the
   // reference's `pointSqDis < minPointSqDis` starting from NEAREST_FEATURE_SEARCH_SQ_DIST.
-  unsigned long long k2 = kKeyMax, k3 = kKeyMax;
-  unsigned s2 = 0xffffffffu, s3 = 0xffffffffu;
-  int q2 = -1, q3 = -1;
+  // a lane serves one ring, hence one class: it keeps a single (best, runner-up, slot) triple
+  unsigned long long kb = kKeyMax;
+  unsigned sb = 0xffffffffu;
+  int qb = -1;
   const int r = cr - 2 + lane / 6, sub = lane % 6;  // 5 rings x 6 lanes
+  const bool cls2 = SURF ? (r == cr) : true;
   if (lane < 30 && r >= 0 && r < ix.nrings && (SURF || r != cr)) {
-    const bool cls2 = SURF ? (r == cr) : true;
     const int win = cls2 ? w2 : w3;
     const int blo = win >> 16, nbins = win & 0xffff, base = r * ix.nb;
     for (int seg = 0; seg < 2; ++seg) {
@@ -314,12 +328,11 @@ __device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, 
         for (int u = 0; u < 2; ++u) {
           const int pu = p + 6 * u;
           const float4 t = ix.pts[pu < pe ? pu : p];
-          const int j = slot_index(t.w);
-          const bool fwd = j > c;
-          const unsigned long long k = pack_key(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z), fwd ? order_fwd(j) : order_bwd(j));
-          if (pu < pe && j != c && (!fwd || j < fwdBound)) {
-            if (cls2) take(k, pu, k2, s2, q2);
-            else take(k, pu, k3, s3, q3);
+          const unsigned d = __float_as_uint(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z));
+          if (pu < pe && d <= sb) {  // farther than the runner-up: changes nothing (see az_scan_nn_slice)
+            const int j = slot_index(t.w);
+            const bool fwd = j > c;
+            if (j != c && (!fwd || j < fwdBound)) take(((unsigned long long)d << 32) | (fwd ? order_fwd(j) : order_bwd(j)), pu, kb, sb, qb);
           }
         }
       }
@@ -327,6 +340,10 @@ __device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, 
   }
   const float gate = sqrtf(nearf);
   const unsigned nearbits = __float_as_uint(nearf);
+  const bool mine2 = lane < 30 && cls2;  // (lanes outside the 5 x 6 layout hold the neutral triple)
+  unsigned long long k2 = mine2 ? kb : kKeyMax, k3 = mine2 ? kKeyMax : kb;
+  unsigned s2 = mine2 ? sb : 0xffffffffu, s3 = mine2 ? 0xffffffffu : sb;
+  int q2 = mine2 ? qb : -1, q3 = mine2 ? -1 : qb;
   warp_argmin2(k2, s2, q2);
   const bool ok2 = (unsigned)(k2 >> 32) < nearbits && q2 >= 0;
   i2 = ok2 ? order_decode((unsigned)(k2 & 0xffffffffu)) : -1;

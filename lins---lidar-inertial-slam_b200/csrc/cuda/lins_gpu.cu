@@ -7,6 +7,7 @@
 #include <atomic>
 #include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -23,11 +24,11 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------------------
 // dynamic shared memory layout:
-//   [qpt float4 x Q][sel float4 x Q][qa float4 x Q][qw int4 x Q][qref, qref2 float4 x Q][key u64 x Q][pos int x 3Q][qccr int x Q][pos int x 3Q][Smem][azS ..][azC ..]
+//   [qpt float4 x Q][sel float4 x Q][qa float4 x Q][qw int4 x Q][qref, qref2 float4 x Q][key u64 x Q][pos int x 3Q][qccr int x Q][wl int x Q][Smem][azS ..][azC ..]
 // cap_s / cap_c = points of the (ring, azimuth)-sorted target copies kept in shared memory (0: global scratch)
 // ---------------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t smem_front_bytes(int qtile) {
-  size_t b = (size_t)qtile * (16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4);
+  size_t b = (size_t)qtile * (16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4 + 4);
   b = (b + 15) & ~(size_t)15;
   return b + ((sizeof(Smem) + 15) & ~(size_t)15);
 }
@@ -49,7 +50,8 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
   unsigned long long* key = reinterpret_cast<unsigned long long*>(qref2buf + Q);
   int* posbuf = reinterpret_cast<int*>(key + Q);
   int* qccrbuf = posbuf + 3 * Q;
-  size_t off = (size_t)Q * (16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4);
+  int* wlbuf = qccrbuf + Q;
+  size_t off = (size_t)Q * (16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4 + 4);
   off = (off + 15) & ~(size_t)15;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + off);
   float4* az_smem = reinterpret_cast<float4*>(smem_raw + smem_front_bytes(Q));
@@ -65,7 +67,7 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
 
   const long long t_cta0 = clock64();
   PassBuffers pb;
-  pb.qpt = qpt; pb.sel = selbuf; pb.qa = qabuf; pb.qw = qwbuf; pb.qref = qrefbuf; pb.qref2 = qref2buf; pb.qccr = qccrbuf; pb.key = key; pb.pos = posbuf; pb.azS = nullptr; pb.azC = nullptr;
+  pb.qpt = qpt; pb.sel = selbuf; pb.qa = qabuf; pb.qw = qwbuf; pb.qref = qrefbuf; pb.qref2 = qref2buf; pb.qccr = qccrbuf; pb.wl = wlbuf; pb.key = key; pb.pos = posbuf; pb.azS = nullptr; pb.azC = nullptr;
 
   for (;;) {
     if (tid == 0) { sm.scan = atomicAdd(bv.work_counter, 1); sm.tlast = clock64(); }
@@ -263,9 +265,9 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
 // the 3 / 2 matched targets (16 B each), recomputes de-skew, residual, weight and Jacobian row, and reduces
 // the 28 sums per scan with a fixed shuffle tree.  Nothing is staged in shared memory: with >= 4096 resident
 // scans the working set exceeds L2 and the kernel is bound by HBM traffic + f64 issue.
-constexpr int kJacThreads = 256;
-__global__ void __launch_bounds__(kJacThreads) lins_jacobian_kernel(const __grid_constant__ BatchView bv,
-                                                                 const __grid_constant__ KParams kp) {
+template <int kJacThreads, int kJacMinBlocks>
+__global__ void __launch_bounds__(kJacThreads, kJacMinBlocks) lins_jacobian_kernel(const __grid_constant__ BatchView bv,
+                                                                                const __grid_constant__ KParams kp) {
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * kJacThreads) >> 5;
   for (int scan = (blockIdx.x * kJacThreads + threadIdx.x) >> 5; scan < bv.n_scans; scan += warps_per_grid) {
@@ -896,10 +898,21 @@ int lins_gpu_batch_jacobian_pass(lins_ctx* ctx, double* accum_out) {
   BatchView bv = view_of(r, false, false);
   bv.state_in = r.state_out.p;  // linearise at the updated state; IDs = the last iteration's
   KParams kp = make_kparams(ctx->prm, MODE_JACOBIAN, 1);
-  const int warps_needed = r.n;
-  int grid = std::min((warps_needed + (kJacThreads / 32) - 1) / (kJacThreads / 32), ctx->sm_count * 8);
-  if (grid < 1) grid = 1;
-  lins_jacobian_kernel<<<grid, kJacThreads, 0, ctx->stream>>>(bv, kp);
+  // one warp per scan; the occupancy / register trade-off is a launch-bounds choice (LINS_JAC_VARIANT: tuning knob)
+  static const int variant = [] { const char* e = std::getenv("LINS_JAC_VARIANT"); return e ? std::atoi(e) : 0; }();
+  auto go = [&](auto kernel, int threads, int min_blocks) {
+    const int wpb = threads / 32;
+    int grid = std::min((r.n + wpb - 1) / wpb, ctx->sm_count * min_blocks);
+    if (grid < 1) grid = 1;
+    kernel<<<grid, threads, 0, ctx->stream>>>(bv, kp);
+  };
+  switch (variant) {
+    // measured on B200, 5000 scans (408 MB working set): <256,1> 148 us, <128,4> 101 us, <128,5> 94 us, <128,6> 100 us
+    case 1: go(lins_jacobian_kernel<128, 4>, 128, 4); break;
+    case 3: go(lins_jacobian_kernel<128, 6>, 128, 6); break;
+    case 4: go(lins_jacobian_kernel<256, 1>, 256, 8); break;  // round-1 first version: 156 registers, one CTA resident per SM
+    default: go(lins_jacobian_kernel<128, 5>, 128, 5); break;  // 96 registers (324 B of spills), 20 warps per SM
+  }
   CK(cudaGetLastError());
   ctx->launches += 1;
   if (accum_out) {

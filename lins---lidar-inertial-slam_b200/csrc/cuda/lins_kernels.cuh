@@ -115,6 +115,8 @@ struct Smem {
   int azTabS[kAzTabS + 1];  // (ring, azimuth bin) -> first slot of the sorted surf copy
   int azTabC[kAzTabC + 1];
   int scan_tmp[kThreads];
+  int dbg[2];               // diagnostics (only touched when phase timers are enabled)
+  int wl_n[2], wl_head[2];  // work lists of the closest-point / walk phases (entries, next entry to hand out)
   int az_ok;                // 1: both clouds ring-sorted + indexed (fast path); 0: legacy brute-force / plain walks
   int nbS, nbC, nringsS, nringsC;
   unsigned long long mbar;

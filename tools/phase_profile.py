@@ -22,6 +22,5 @@ for k, nm in enumerate(names):
     print(f"  {nm:40s} {100*t[k]/tot:5.1f}%   {per:9.0f} cycles per {'scan' if k in (0,9) else 'iteration'}")
 print("serial tail per iteration: sums+A6 %.0f | M6+LU %.0f | K x, norms %.0f | logic+boxPlus %.0f | next consts+boxMinus %.0f | barrier %.0f" % (t[18]/its, t[19]/its, t[21]/its, t[23]/its, t[25]/its, t[8]/its))
 print("first iteration %.0f cycles/scan | CTA busy: mean %.3e max %.3e (tail %.1f%%)" % (t[24]/n, t[26]/148, t[27], 100*(1-t[26]/148/max(t[27],1))))
-print("certificates: all %d  closest-only %d  full %d | non-certified with positive slack: %d, mean moved %.4f m, mean slack %.4f m" % (t[10], t[11], t[12], t[15], t[13]/max(t[15],1)/1e4, t[14]/max(t[15],1)/1e4))
-print("sub-phases per iteration: P1 %.0f  P2 %.0f  P3 %.0f  P4 %.0f cycles" % (t[20]/its, t[4]/its, t[22]/its, t[5]/its))
-print("P2 scans: %d (%.1f per iteration), mean cycles per scan %.0f, scans with >= 64 bins: %d" % (t[17], t[17]/its, 16*t[16]/max(t[17],1), t[13]))
+print("work lists per iteration: closest-point searches %.1f (ring-bins per search %.1f; first pass %.1f), walk searches %.1f (ring-bins per search %.1f; first pass %.1f)" % (
+    t[10]/its, t[12]/max(t[10],1), t[14]/max(n,1)/550, t[11]/its, t[13]/max(t[11],1), t[15]/max(n,1)/550))
