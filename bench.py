@@ -181,12 +181,15 @@ def main():
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
+    # one stream per resident batch: consecutive steps touch different batches, so the persistent kernel of step k+1
+    # moves onto the SMs that step k's last (longest) scans no longer occupy instead of waiting for the whole grid
+    NB = 3
+    bstreams = [torch.cuda.Stream(device=local) for _ in range(NB)]
 
     # ---- inputs: 3 resident batches of `scans` units each; weak scaling = different seeds per rank ----------
-    NB = 3
     n = args.scans
     batches = [synth.generate("config3", n=n, seed0=1000 + 100000 * rank + 10000 * k) for k in range(NB)]
-    ctxs = [capi.LinsGpu(prm, device=local, stream=stream.cuda_stream) for _ in range(NB)]
+    ctxs = [capi.LinsGpu(prm, device=local, stream=bstreams[k].cuda_stream) for k in range(NB)]
     for c, b in zip(ctxs, batches):
         c.batch_upload(b)
     torch.cuda.synchronize()
@@ -199,15 +202,17 @@ def main():
     for c in ctxs:
         p, nn = c.batch_results_device()
         res_views.append(torch.as_tensor(_DevView(p, nn * 64), device=f"cuda:{local}"))
-    gathered = torch.empty(world * n * 64, dtype=torch.uint8, device=f"cuda:{local}") if world > 1 else None
+
+    gathered = [torch.empty(world * n * 64, dtype=torch.uint8, device=f"cuda:{local}") for _ in range(NB)] if world > 1 else None
 
     def step(k):
-        c = ctxs[k % NB]
-        c.batch_run()  # one fused kernel launch on torch's current stream
-        if world > 1:  # the path's only exchange: the pose gather (64 B / scan)
-            dist.all_gather_into_tensor(gathered, res_views[k % NB])
+        j = k % NB
+        with torch.cuda.stream(bstreams[j]):
+            ctxs[j].batch_run()  # one fused kernel launch on that batch's stream
+            if world > 1:  # the path's only exchange: the pose gather (64 B / scan), ordered after the kernel on the same stream
+                dist.all_gather_into_tensor(gathered[j], res_views[j])
 
-    for k in range(args.warmup):
+    for k in range(max(args.warmup, NB)):
         step(k)
     torch.cuda.synchronize()
     iters_per_batch, iters_per_scan = [], []
@@ -225,22 +230,25 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(stream)  # the device is idle here; every batch stream starts after this event ...
+    for st in bstreams:
+        st.wait_event(e0)
     for k in range(args.steps):
-        ev[k][0].record()
-        ctxs[k % NB].batch_run()
-        ev[k][1].record()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, res_views[k % NB])
-    e1.record()
+        step(k)
+    for st in bstreams:  # ... and the end event waits for all of them
+        done = torch.cuda.Event()
+        done.record(st)
+        stream.wait_event(done)
+    e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clk = clocks.stop() if rank == 0 else None
     elapsed_ms = e0.elapsed_time(e1)
-    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    # launches of consecutive steps overlap at their tails, so a per-launch event pair would also count the time a
+    # launch waits for SMs: the effective duration per launch is the timed region divided by its launches
+    kernel_ms = [elapsed_ms / args.steps] * args.steps
     launches = sum(c.launch_count() for c in ctxs) - launches0
     my_iters = sum(iters_per_batch[k % NB] for k in range(args.steps))
     t = torch.tensor([elapsed_ms, float(my_iters), float(launches)], dtype=torch.float64, device=f"cuda:{local}")
@@ -253,20 +261,33 @@ def main():
     value = total_iters / (elapsed_ms * 1e-3)
 
     # ---- end to end through the C-ABI with host buffers (pack + H2D + kernel + D2H timed) ------------------------
-    e2e_ctx = ctxs[0]
-    e2e_steps = max(3, min(args.steps, 10))
-    for b in batches:  # warm: pinned staging grows to the largest batch before the timed region
-        e2e_ctx.ieskf_batch(b)
+    # The user-facing call is lins_gpu_ieskf_batch(ctx, host batch) -> host results (synchronous: pack, H2D, the
+    # fused kernel, D2H).  A replay job keeps NB contexts busy from NB host threads (ctypes drops the GIL), so one
+    # batch's packing / PCIe traffic overlaps another's kernel; every step still moves all its bytes both ways.
+    import threading
+    e2e_steps = max(NB, min(args.steps, 12))
+    for c in ctxs:
+        for b in batches:  # warm: each context's pinned staging grows to the largest batch before the timed region
+            c.ieskf_batch(b)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    e2e_counts = [0] * NB
+
+    def e2e_worker(j):
+        for k in range(j, e2e_steps, NB):
+            _, _, res = ctxs[j].ieskf_batch(batches[k % NB])
+            e2e_counts[j] += int(res["iters"].sum())
+
+    workers = [threading.Thread(target=e2e_worker, args=(j,)) for j in range(NB)]
     t0 = time.perf_counter()
-    e2e_iters = 0
-    for k in range(e2e_steps):
-        _, _, res = e2e_ctx.ieskf_batch(batches[k % NB])
-        e2e_iters += int(res["iters"].sum())
+    for w in workers:
+        w.start()
+    for w in workers:
+        w.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_iters = sum(e2e_counts)
     te = torch.tensor([e2e_s, float(e2e_iters)], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
@@ -329,9 +350,10 @@ def main():
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 (f32 association)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "scans_per_gpu_per_step": n, "iterations_per_step_rank0": float(np.mean(iters_per_batch)),
-                   "l2": f"{NB} resident batches used round-robin ({NB} x {h2d / 1e6:.0f} MB > 126 MB L2)", "parallelism": f"scan-sharded x{world}, pose all_gather per step" if world > 1 else "1 GPU"},
+                   "l2": f"{NB} resident batches used round-robin ({NB} x {h2d / 1e6:.0f} MB > 126 MB L2)", "parallelism": f"scan-sharded x{world}, pose all_gather per step" if world > 1 else "1 GPU",
+                   "streams": f"one CUDA stream per resident batch ({NB}): consecutive steps overlap at their kernel tails; e2e = {NB} host threads, one context each"},
         "clocks": clk,
-        "e2e": {"value": e2e_iters / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "e2e": {"value": e2e_iters / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "host_threads": NB},
         "gpu_launches": int(total_launches),
         "roofline": roofline, "roofline_jacobian": roofline_j,
     }

@@ -171,7 +171,7 @@ int lins_gpu_batch_jacobian_pass(lins_ctx* ctx, double* accum_out /*n x 29 or NU
 int lins_gpu_sync(lins_ctx* ctx);
 
 /* diagnostics: per-phase SM-cycle counters of the fused kernel (enable, then read after a batch_run) */
-int lins_gpu_debug_phase_cycles(lins_ctx* ctx, int enable, long long* out /*32 or NULL*/);
+int lins_gpu_debug_phase_cycles(lins_ctx* ctx, int enable, long long* out /*64 or NULL*/);
 
 /* kernels launched by this ctx since creation (for bench.py's gpu_launches). */
 int64_t lins_gpu_launch_count(const lins_ctx* ctx);

@@ -126,7 +126,7 @@ class LinsGpu:
         self._ck(self.L.lins_gpu_sync(self.h))
 
     def phase_cycles(self, enable=True, read=False):
-        out = np.zeros(32, np.int64) if read else None
+        out = np.zeros(64, np.int64) if read else None
         self._ck(self.L.lins_gpu_debug_phase_cycles(self.h, int(enable), ptr(out)))
         return out
 

@@ -10,6 +10,13 @@
 
 namespace lins_dev {
 
+// Probe-first search (lins_assoc_az.cuh: az_probe_window).  Measured on the VLP-16 workload: it pays for the closest-
+// point search of a scan's FIRST pass (every query is unseeded, all warps are busy, the phase is issue bound:
+// 176 K -> 104 K cycles per scan) and costs time everywhere else (later passes and the walks are bound by the latency
+// of a few lone searches, which a second scan only lengthens).
+constexpr bool kProbeNN = true;
+constexpr bool kProbeWalk = false;
+
 struct PassBuffers {
   float4* qpt;               // staged queries (x, y, z, intensity) of the current tile
   float4* sel;               // de-skewed queries (pointSel)
@@ -117,12 +124,16 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
       const float gate = sqrtf(nearf);
       // P2: warps pull queries from the work list (the per-query cost is heavy-tailed; a static split leaves warps idle)
       for (;;) {
+        const long long t_f0 = bv.timers ? clock64() : 0;
+        long long tmv[2] = {0, 0};
+        long long* tm = bv.timers ? tmv : nullptr;
         int k = 0;
         if (lane == 0) k = atomicAdd(&sm.wl_head[0], 1);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= sm.wl_n[0]) break;
         const int i = pb.wl[k];
         int w1 = pb.qw[i].x;
+        const long long t_s0 = (bv.timers && lane == 0) ? clock64() : 0;
         unsigned long long k1 = kKeyMax;
         unsigned second = 0xffffffffu;
         int p1 = -1;
@@ -131,7 +142,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         const float4 s = pb.sel[i];
         float4 qa = pb.qa[i];
         if (w1 >= 0) {
-          const int wp = az_probe_window(ix, qa, w1);
+          const int wp = first_pass_of_scan ? az_probe_window<kProbeNN>(ix, qa, w1) : -1;
           if (wp >= 0) {  // wide window (no usable previous answer): probe first, then search inside the implied window
             az_scan_nn(ix, s, wp, p1, second);
             if (p1 >= 0) {
@@ -139,7 +150,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
               if (lane == 0) pb.qa[i] = qa;
             }
           }
-          k1 = az_scan_nn(ix, s, w1, p1, second);
+          k1 = az_scan_nn(ix, s, w1, p1, second, tm);
         }
         if (lane == 0) {
           const float d1 = __uint_as_float((unsigned)(k1 >> 32));
@@ -147,10 +158,24 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
           pb.qref[i] = make_float4(s.x, s.y, s.z, w1 >= 0 ? search_slack((unsigned)(k1 >> 32), second, qa.w, gate, acc1) : -1.f);
           pb.pos[3 * i] = acc1 ? p1 : -1;
           pb.qccr[i] = acc1 ? ((slot_ring(ix.pts[p1].w) << 24) | (int)(unsigned)(k1 & 0xffffffffu)) : -1;
+          if (bv.timers && !first_pass_of_scan) {
+            const unsigned long long dt = (unsigned long long)(clock64() - t_s0);
+            atomicAdd((unsigned long long*)&bv.timers[20], dt);
+            atomicMax((unsigned long long*)&bv.timers[22], dt);
+            const long long t_e = clock64();
+            if (w1 >= 0) {  // fetch+loads | setup+loop | arg-min | epilogue
+              atomicAdd((unsigned long long*)&bv.timers[32], (unsigned long long)(t_s0 - t_f0));
+              atomicAdd((unsigned long long*)&bv.timers[33], (unsigned long long)(tmv[0] - t_s0));
+              atomicAdd((unsigned long long*)&bv.timers[34], (unsigned long long)(tmv[1] - tmv[0]));
+              atomicAdd((unsigned long long*)&bv.timers[35], (unsigned long long)(t_e - tmv[1]));
+              atomicAdd((unsigned long long*)&bv.timers[36], 1ull);
+            }
+            if (w1 >= 0 && (w1 & 0xffff) >= 64) { atomicAdd((unsigned long long*)&bv.timers[16], dt); atomicAdd((unsigned long long*)&bv.timers[17], 1ull); }
+          }
         }
       }
       __syncthreads();
-      LINS_TICK(4);
+      LINS_TICK_F(4, 28, first_pass_of_scan);
       for (int i = threadIdx.x; i < nq; i += kThreads) {  // P3
         const int lvl = pb.qw[i].x;
         if (lvl == -2) continue;
@@ -188,6 +213,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         if (k >= sm.wl_n[1]) break;
         const int i = pb.wl[k];
         const int4 w = pb.qw[i];
+        const long long t_s0 = (bv.timers && lane == 0) ? clock64() : 0;
         const bool surf = i < nsT;
         const int gq = q0 + i;
         float2 B = reinterpret_cast<const float2*>(pb.key)[i];
@@ -197,7 +223,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         {  // wide windows (no usable previous answer): probe a small window first and re-window from what it finds
           const float4 qa = pb.qa[i];
           const int wide = max(w2 & 0xffff, surf ? (w3 & 0xffff) : 0);
-          const int wp = az_probe_window(surf ? ixS : ixC, qa, wide);
+          const int wp = az_probe_window<kProbeWalk>(surf ? ixS : ixC, qa, wide);
           if (wp >= 0) {
             const int c = w.w & 0x00ffffff, cr = (int)((unsigned)w.w >> 24);
             const int sd2 = seeded ? pb.pos[3 * i + 1] : -1, sd3 = seeded ? pb.pos[3 * i + 2] : -1;
@@ -219,6 +245,11 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         if (lane == 0) {
           pb.pos[3 * i + 1] = p2; pb.pos[3 * i + 2] = p3;
           pb.qref2[i] = make_float4(s.x, s.y, s.z, slack);
+          if (bv.timers && !first_pass_of_scan) {
+            const unsigned long long dt = (unsigned long long)(clock64() - t_s0);
+            atomicAdd((unsigned long long*)&bv.timers[30], dt);
+            if (max(w2 & 0xffff, w3 & 0xffff) >= 64) atomicAdd((unsigned long long*)&bv.timers[31], dt);
+          }
           const int i1 = w.w & 0x00ffffff;
           if (surf) { int* o = bv.ind_s + 3 * (size_t)(qs0 + gq); o[0] = i1; o[1] = i2; o[2] = i3; }
           else { int* o = bv.ind_c + 2 * (size_t)(qc0 + gq - ns); o[0] = i1; o[1] = i2; }
@@ -264,7 +295,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
       }
     }
     __syncthreads();
-    LINS_TICK(5);
+    LINS_TICK_F(5, 29, first_pass_of_scan);
     // ---- A5/A6 residuals + A7-A9 fold ------------------------------------------------------------------------------
     // tripod points: fast path -> slots of the sorted copies; otherwise original indices into the walk clouds.
     // (fast path with several tiles on a non-search iteration falls back to original indices, see above)

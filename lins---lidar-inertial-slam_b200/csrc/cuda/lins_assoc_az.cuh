@@ -124,7 +124,10 @@ __device__ __forceinline__ void az_window(int nb, float aq, float th, int& blo, 
 __device__ __forceinline__ int slot_index(float w) { return __float_as_int(w) & 0x00ffffff; }
 __device__ __forceinline__ int slot_ring(float w) { return (int)((unsigned)__float_as_int(w) >> 24); }
 __device__ __forceinline__ int pack_window(int blo, int nbins) { return (blo << 16) | nbins; }
-constexpr float kCertMargin = 0.1f;  // metres added to every search radius so that certificates have room
+#ifndef LINS_CERT_MARGIN
+#define LINS_CERT_MARGIN 0.1f
+#endif
+constexpr float kCertMargin = LINS_CERT_MARGIN;  // metres added to every search radius so that certificates have room
 // bound used to build a window: (sqrt(U) + margin)^2
 __device__ __forceinline__ float widen(float U) { const float r = sqrtf(U) + kCertMargin; return r * r; }
 // slack (metres) of one search: winner / runner-up as f32 squared-distance BITS (0xffffffff = none), Bout = distance
@@ -180,9 +183,9 @@ __device__ __forceinline__ int az_prepare_nn(const AzIndex& ix, const float4 s, 
 // than the window of this radius first scans the small window; the best candidate found there is a real target,
 // so its distance is a valid upper bound and the exact search runs inside the (much smaller) window it implies.
 constexpr float kProbeSq = 0.25f;  // (0.5 m)^2
-constexpr bool kUseProbe = false;  // measured slower on the VLP-16 workload (per-query cost is latency, not candidates)
+template <bool ENABLED>
 __device__ __forceinline__ int az_probe_window(const AzIndex& ix, const float4 qa, int full_window) {
-  if (!kUseProbe) return -1;
+  if (!ENABLED) return -1;
   int blo, nbins;
   az_window(ix.nb, qa.x, az_halfwidth(kProbeSq, qa.y), blo, nbins);
   return (full_window & 0xffff) > 2 * nbins + 4 ? pack_window(blo, nbins) : -1;
@@ -195,28 +198,37 @@ __device__ __forceinline__ void take(unsigned long long k, int p, unsigned long 
   if (k < best) { second = (unsigned)(best >> 32); best = k; bpos = p; }
   else { const unsigned d = (unsigned)(k >> 32); second = d < second ? d : second; }
 }
-// A candidate farther than the lane's current runner-up can change neither its best nor its runner-up (`second` is
-// never below the best's distance), so the common case costs the distance and one compare; four candidates per lane
-// are in flight per trip (the scan is latency / issue bound, not bandwidth bound).
+// Branch-free bookkeeping of (best key, its slot, runner-up distance): a lone warp runs these scans with nothing to
+// hide latency behind, so the loop body is straight-line code with independent chains (four candidates per lane per
+// trip, reduced as a small tournament) instead of data-dependent branches.
+//   keep(a, b): a <- min(a, b) (with its slot), returns the distance bits of the loser
+__device__ __forceinline__ unsigned keep_min(unsigned long long& a, int& pa, unsigned long long b, int pb) {
+  const bool lt = b < a;
+  const unsigned loser = (unsigned)((lt ? a : b) >> 32);
+  a = lt ? b : a;
+  pa = lt ? pb : pa;
+  return loser;
+}
 template <int LPR>
 __device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4 s, int p, int pe, unsigned long long& best,
                                                  unsigned& second, int& bpos) {
   for (; p < pe; p += 4 * LPR) {
-    float4 t[4];
-    unsigned d[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int pu = p + u * LPR; t[u] = ix.pts[pu < pe ? pu : p]; }
+    unsigned long long k[4];
+    int q[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      d[u] = __float_as_uint(sqdist_f32(s.x, s.y, s.z, t[u].x, t[u].y, t[u].z));
-      if (p + u * LPR >= pe) d[u] = 0xffffffffu;  // (0xffffffff is never <= a runner-up that a real candidate has set)
+      const int pu = p + u * LPR;
+      const bool valid = pu < pe;
+      const float4 t = ix.pts[valid ? pu : p];
+      const unsigned d = __float_as_uint(sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z));
+      k[u] = valid ? (((unsigned long long)d << 32) | (unsigned)slot_index(t.w)) : kKeyMax;  // (kKeyMax never wins and never lowers a runner-up)
+      q[u] = pu;
     }
-    const unsigned dmin = min(min(d[0], d[1]), min(d[2], d[3]));
-    if (dmin <= second) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (p + u * LPR < pe && d[u] <= second) take(((unsigned long long)d[u] << 32) | (unsigned)slot_index(t[u].w), p + u * LPR, best, second, bpos);
-    }
+    const unsigned l01 = keep_min(k[0], q[0], k[1], q[1]);
+    const unsigned l23 = keep_min(k[2], q[2], k[3], q[3]);
+    const unsigned l03 = keep_min(k[0], q[0], k[2], q[2]);
+    const unsigned lb = keep_min(best, bpos, k[0], q[0]);
+    second = min(min(second, lb), min(min(l01, l23), l03));
   }
 }
 // warp arg-min that also yields the distance bits of the overall runner-up
@@ -232,7 +244,8 @@ __device__ __forceinline__ void warp_argmin2(unsigned long long& best, unsigned&
   best = ((unsigned long long)mhi << 32) | mlo;
 }
 template <int LPR>
-__device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, const float4 s, int win, int& pos, unsigned& second_out) {
+__device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, const float4 s, int win, int& pos, unsigned& second_out,
+                                                           long long* tm = nullptr) {
   const int lane = threadIdx.x & 31;
   const int blo = win >> 16, nbins = win & 0xffff;
   constexpr int RPP = 32 / LPR;
@@ -249,16 +262,19 @@ __device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, co
       if (e1 > 0) az_scan_nn_slice<LPR>(ix, s, ix.bstart[base] + sub, ix.bstart[base + e1], best, second, bpos);
     }
   }
+  if (tm) tm[0] = clock64();
   warp_argmin2(best, second, bpos);
   if ((unsigned)(best >> 32) >= 0x7f800000u) { best = kKeyMax; bpos = -1; }  // only inf / NaN distances: nothing found
   pos = bpos;
   second_out = second;
+  if (tm) tm[1] = clock64();
   return best;
 }
-__device__ __forceinline__ unsigned long long az_scan_nn(const AzIndex& ix, const float4 s, int win, int& pos, unsigned& second) {
-  if (ix.nrings <= 8) return az_scan_nn_t<4>(ix, s, win, pos, second);
-  if (ix.nrings <= 16) return az_scan_nn_t<2>(ix, s, win, pos, second);
-  return az_scan_nn_t<1>(ix, s, win, pos, second);
+__device__ __forceinline__ unsigned long long az_scan_nn(const AzIndex& ix, const float4 s, int win, int& pos, unsigned& second,
+                                                         long long* tm = nullptr) {
+  if (ix.nrings <= 8) return az_scan_nn_t<4>(ix, s, win, pos, second, tm);
+  if (ix.nrings <= 16) return az_scan_nn_t<2>(ix, s, win, pos, second, tm);
+  return az_scan_nn_t<1>(ix, s, win, pos, second, tm);
 }
 
 // ---- phase P3 (one THREAD per query): bound + window the walks of a query whose closest point is (c, cr) -------
@@ -329,11 +345,11 @@ __device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, 
           const int pu = p + 6 * u;
           const float4 t = ix.pts[pu < pe ? pu : p];
           const unsigned d = __float_as_uint(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z));
-          if (pu < pe && d <= sb) {  // farther than the runner-up: changes nothing (see az_scan_nn_slice)
-            const int j = slot_index(t.w);
-            const bool fwd = j > c;
-            if (j != c && (!fwd || j < fwdBound)) take(((unsigned long long)d << 32) | (fwd ? order_fwd(j) : order_bwd(j)), pu, kb, sb, qb);
-          }
+          const int j = slot_index(t.w);
+          const bool fwd = j > c;
+          const bool adm = pu < pe && j != c && (!fwd || j < fwdBound);
+          const unsigned long long k = adm ? (((unsigned long long)d << 32) | (fwd ? order_fwd(j) : order_bwd(j))) : kKeyMax;
+          sb = min(sb, keep_min(kb, qb, k, pu));  // branch-free, see az_scan_nn_slice
         }
       }
     }

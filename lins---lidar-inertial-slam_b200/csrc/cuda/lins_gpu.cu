@@ -825,8 +825,8 @@ int lins_gpu_batch_run(lins_ctx* ctx) {
   CK(cudaSetDevice(ctx->device));
   BatchView bv = view_of(r, true, false);
   if (ctx->timers_on) {
-    CK(r.timers.reserve(32));
-    CK(cudaMemsetAsync(r.timers.p, 0, sizeof(long long) * 32, ctx->stream));
+    CK(r.timers.reserve(64));
+    CK(cudaMemsetAsync(r.timers.p, 0, sizeof(long long) * 64, ctx->stream));
     bv.timers = r.timers.p;
   }
   return launch(ctx, bv, make_kparams(ctx->prm, MODE_IESKF, 0));
@@ -876,7 +876,7 @@ int lins_gpu_debug_phase_cycles(lins_ctx* ctx, int enable, long long* out) {
   if (out) {
     if (!ctx->batch.timers.p) return fail(ctx, LINS_E_INVALID, "timers were not enabled for the last run");
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(out, ctx->batch.timers.p, sizeof(long long) * 32, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, ctx->batch.timers.p, sizeof(long long) * 64, cudaMemcpyDeviceToHost));
   }
   ctx->timers_on = enable != 0;
   return LINS_OK;

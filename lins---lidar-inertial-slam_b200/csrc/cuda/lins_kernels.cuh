@@ -134,6 +134,17 @@ struct Smem {
     }                                                                                  \
   } while (0)
 
+// same, and the interval is also added to slot kf when `first` holds (first pass of a scan)
+#define LINS_TICK_F(k, kf, first)                                                       \
+  do {                                                                                 \
+    if (bv.timers && threadIdx.x == 0) {                                               \
+      const long long _t = clock64();                                                  \
+      atomicAdd((unsigned long long*)&bv.timers[k], (unsigned long long)(_t - sm.tlast)); \
+      if (first) atomicAdd((unsigned long long*)&bv.timers[kf], (unsigned long long)(_t - sm.tlast)); \
+      sm.tlast = _t;                                                                   \
+    }                                                                                  \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------------------
 // per-iteration constants (thread 0)
 __device__ void compute_iter_consts(Smem& sm) {
