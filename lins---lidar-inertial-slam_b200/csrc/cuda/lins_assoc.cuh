@@ -14,6 +14,10 @@ namespace lins_dev {
 // point search of a scan's FIRST pass (every query is unseeded, all warps are busy, the phase is issue bound:
 // 176 K -> 104 K cycles per scan) and costs time everywhere else (later passes and the walks are bound by the latency
 // of a few lone searches, which a second scan only lengthens).
+#ifndef LINS_SEARCH_DIAG
+#define LINS_SEARCH_DIAG 0
+#endif
+constexpr bool kSearchDiag = LINS_SEARCH_DIAG != 0;  // per-search cycle counters for tools/phase_profile.py
 constexpr bool kProbeNN = true;
 constexpr bool kProbeWalk = false;
 
@@ -57,6 +61,8 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
   const bool seeded = fast && !first_pass_of_scan && ntot <= bv.qtile;
 
   AzIndex ixS, ixC;
+  ixS.sbase = Ts <= bv.cap_s ? smem_u32(pb.azS) : 0u;
+  ixC.sbase = Tc <= bv.cap_c ? smem_u32(pb.azC) : 0u;
   ixS.pts = pb.azS; ixS.bstart = sm.azTabS; ixS.nb = sm.nbS; ixS.nrings = sm.nringsS; ixS.T = Ts;
   ixC.pts = pb.azC; ixC.bstart = sm.azTabC; ixC.nb = sm.nbC; ixC.nrings = sm.nringsC; ixC.T = Tc;
 
@@ -124,16 +130,17 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
       const float gate = sqrtf(nearf);
       // P2: warps pull queries from the work list (the per-query cost is heavy-tailed; a static split leaves warps idle)
       for (;;) {
-        const long long t_f0 = bv.timers ? clock64() : 0;
-        long long tmv[2] = {0, 0};
-        long long* tm = bv.timers ? tmv : nullptr;
+        const bool diag = kSearchDiag && bv.timers != nullptr;  // per-search clocks: compiled out unless -DLINS_SEARCH_DIAG=1
+        const long long t_f0 = diag ? clock64() : 0;
+        long long tmv[4] = {0, 0, 0, 0};
+        long long* tm = diag ? tmv : nullptr;
         int k = 0;
         if (lane == 0) k = atomicAdd(&sm.wl_head[0], 1);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= sm.wl_n[0]) break;
         const int i = pb.wl[k];
         int w1 = pb.qw[i].x;
-        const long long t_s0 = (bv.timers && lane == 0) ? clock64() : 0;
+        const long long t_s0 = (diag && lane == 0) ? clock64() : 0;
         unsigned long long k1 = kKeyMax;
         unsigned second = 0xffffffffu;
         int p1 = -1;
@@ -158,7 +165,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
           pb.qref[i] = make_float4(s.x, s.y, s.z, w1 >= 0 ? search_slack((unsigned)(k1 >> 32), second, qa.w, gate, acc1) : -1.f);
           pb.pos[3 * i] = acc1 ? p1 : -1;
           pb.qccr[i] = acc1 ? ((slot_ring(ix.pts[p1].w) << 24) | (int)(unsigned)(k1 & 0xffffffffu)) : -1;
-          if (bv.timers && !first_pass_of_scan) {
+          if (diag && !first_pass_of_scan) {
             const unsigned long long dt = (unsigned long long)(clock64() - t_s0);
             atomicAdd((unsigned long long*)&bv.timers[20], dt);
             atomicMax((unsigned long long*)&bv.timers[22], dt);
@@ -169,6 +176,8 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
               atomicAdd((unsigned long long*)&bv.timers[34], (unsigned long long)(tmv[1] - tmv[0]));
               atomicAdd((unsigned long long*)&bv.timers[35], (unsigned long long)(t_e - tmv[1]));
               atomicAdd((unsigned long long*)&bv.timers[36], 1ull);
+              atomicAdd((unsigned long long*)&bv.timers[37], (unsigned long long)tmv[2]);
+              atomicAdd((unsigned long long*)&bv.timers[38], (unsigned long long)tmv[3]);
             }
             if (w1 >= 0 && (w1 & 0xffff) >= 64) { atomicAdd((unsigned long long*)&bv.timers[16], dt); atomicAdd((unsigned long long*)&bv.timers[17], 1ull); }
           }
@@ -213,7 +222,8 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         if (k >= sm.wl_n[1]) break;
         const int i = pb.wl[k];
         const int4 w = pb.qw[i];
-        const long long t_s0 = (bv.timers && lane == 0) ? clock64() : 0;
+        const bool diag = kSearchDiag && bv.timers != nullptr;
+        const long long t_s0 = (diag && lane == 0) ? clock64() : 0;
         const bool surf = i < nsT;
         const int gq = q0 + i;
         float2 B = reinterpret_cast<const float2*>(pb.key)[i];
@@ -245,7 +255,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         if (lane == 0) {
           pb.pos[3 * i + 1] = p2; pb.pos[3 * i + 2] = p3;
           pb.qref2[i] = make_float4(s.x, s.y, s.z, slack);
-          if (bv.timers && !first_pass_of_scan) {
+          if (diag && !first_pass_of_scan) {
             const unsigned long long dt = (unsigned long long)(clock64() - t_s0);
             atomicAdd((unsigned long long*)&bv.timers[30], dt);
             if (max(w2 & 0xffff, w3 & 0xffff) >= 64) atomicAdd((unsigned long long*)&bv.timers[31], dt);

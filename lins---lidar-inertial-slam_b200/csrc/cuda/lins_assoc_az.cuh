@@ -32,6 +32,7 @@ namespace lins_dev {
 
 struct AzIndex {
   const float4* pts;  // sorted copy (shared or global)
+  unsigned sbase;     // its shared-window address when it lives in shared memory, else 0
   const int* bstart;  // [nrings * nb + 1], shared
   int nb, nrings, T;
 };
@@ -209,17 +210,32 @@ __device__ __forceinline__ unsigned keep_min(unsigned long long& a, int& pa, uns
   pa = lt ? pb : pa;
   return loser;
 }
-template <int LPR>
+// One slot of the sorted copy.  When the copy is in shared memory the load is an explicit ld.shared: the generic
+// load the compiler would otherwise emit has a longer latency and was scheduled one candidate at a time (all four
+// loads of a trip through the same registers), which left a lone warp waiting ~100 cycles per candidate.
+template <bool SMEM>
+__device__ __forceinline__ float4 ld_slot(const AzIndex& ix, int p) {
+  if (SMEM) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ix.sbase + 16u * (unsigned)p));
+    return v;
+  }
+  return ix.pts[p];
+}
+template <int LPR, bool SMEM>
 __device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4 s, int p, int pe, unsigned long long& best,
                                                  unsigned& second, int& bpos) {
   for (; p < pe; p += 4 * LPR) {
     unsigned long long k[4];
     int q[4];
+    float4 tt[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) tt[u] = ld_slot<SMEM>(ix, p + u * LPR < pe ? p + u * LPR : p);  // four loads in flight
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int pu = p + u * LPR;
       const bool valid = pu < pe;
-      const float4 t = ix.pts[valid ? pu : p];
+      const float4 t = tt[u];
       const unsigned d = __float_as_uint(sqdist_f32(s.x, s.y, s.z, t.x, t.y, t.z));
       k[u] = valid ? (((unsigned long long)d << 32) | (unsigned)slot_index(t.w)) : kKeyMax;  // (kKeyMax never wins and never lowers a runner-up)
       q[u] = pu;
@@ -243,7 +259,7 @@ __device__ __forceinline__ void warp_argmin2(unsigned long long& best, unsigned&
   payload = __shfl_sync(0xffffffffu, payload, wl);
   best = ((unsigned long long)mhi << 32) | mlo;
 }
-template <int LPR>
+template <int LPR, bool SMEM>
 __device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, const float4 s, int win, int& pos, unsigned& second_out,
                                                            long long* tm = nullptr) {
   const int lane = threadIdx.x & 31;
@@ -254,15 +270,17 @@ __device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, co
   unsigned second = 0xffffffffu;
   int bpos = -1;
   const int e0 = min(blo + nbins, ix.nb), e1 = blo + nbins - ix.nb;
+  int dbg_cand = 0;
   for (int rbase = 0; rbase < ix.nrings; rbase += RPP) {
     const int r = rbase + lane / LPR;
     if (r < ix.nrings) {
       const int base = r * ix.nb;
-      az_scan_nn_slice<LPR>(ix, s, ix.bstart[base + blo] + sub, ix.bstart[base + e0], best, second, bpos);
-      if (e1 > 0) az_scan_nn_slice<LPR>(ix, s, ix.bstart[base] + sub, ix.bstart[base + e1], best, second, bpos);
+      if (tm) { dbg_cand += max(0, (ix.bstart[base + e0] - ix.bstart[base + blo] - sub + LPR - 1) / LPR); if (e1 > 0) dbg_cand += max(0, (ix.bstart[base + e1] - ix.bstart[base] - sub + LPR - 1) / LPR); }
+      az_scan_nn_slice<LPR, SMEM>(ix, s, ix.bstart[base + blo] + sub, ix.bstart[base + e0], best, second, bpos);
+      if (e1 > 0) az_scan_nn_slice<LPR, SMEM>(ix, s, ix.bstart[base] + sub, ix.bstart[base + e1], best, second, bpos);
     }
   }
-  if (tm) tm[0] = clock64();
+  if (tm) { tm[0] = clock64(); tm[2] = __reduce_max_sync(0xffffffffu, (unsigned)dbg_cand); tm[3] = __reduce_add_sync(0xffffffffu, (unsigned)dbg_cand); }
   warp_argmin2(best, second, bpos);
   if ((unsigned)(best >> 32) >= 0x7f800000u) { best = kKeyMax; bpos = -1; }  // only inf / NaN distances: nothing found
   pos = bpos;
@@ -272,9 +290,14 @@ __device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, co
 }
 __device__ __forceinline__ unsigned long long az_scan_nn(const AzIndex& ix, const float4 s, int win, int& pos, unsigned& second,
                                                          long long* tm = nullptr) {
-  if (ix.nrings <= 8) return az_scan_nn_t<4>(ix, s, win, pos, second, tm);
-  if (ix.nrings <= 16) return az_scan_nn_t<2>(ix, s, win, pos, second, tm);
-  return az_scan_nn_t<1>(ix, s, win, pos, second, tm);
+  if (ix.sbase) {
+    if (ix.nrings <= 8) return az_scan_nn_t<4, true>(ix, s, win, pos, second, tm);
+    if (ix.nrings <= 16) return az_scan_nn_t<2, true>(ix, s, win, pos, second, tm);
+    return az_scan_nn_t<1, true>(ix, s, win, pos, second, tm);
+  }
+  if (ix.nrings <= 8) return az_scan_nn_t<4, false>(ix, s, win, pos, second, tm);
+  if (ix.nrings <= 16) return az_scan_nn_t<2, false>(ix, s, win, pos, second, tm);
+  return az_scan_nn_t<1, false>(ix, s, win, pos, second, tm);
 }
 
 // ---- phase P3 (one THREAD per query): bound + window the walks of a query whose closest point is (c, cr) -------
@@ -318,8 +341,8 @@ __device__ __forceinline__ void az_prepare_walk(const AzIndex& ix, const float4 
 // ---- phase P4 (one WARP per query): the ring walks inside their windows -------------------------------------------
 // SURF: Ind2 over ring cr (window w2), Ind3 over rings cr-2, cr-1, cr+1, cr+2 (window w3).  Corner: Ind2 over rings
 // cr-2, cr-1, cr+1, cr+2 (window w2).  Forward candidates (original index j > c) count only while j < fwdBound.
-template <bool SURF>
-__device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
+template <bool SURF, bool SMEM>
+__device__ __forceinline__ void az_scan_walk_t(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
                                              float B2, float B3, int& i2, int& i3, int& pos2, int& pos3, float& slack) {
   const int lane = threadIdx.x & 31;
   const int c = ccr & 0x00ffffff, cr = (int)((unsigned)ccr >> 24);
@@ -340,10 +363,13 @@ __device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, 
       if (seg == 0) { p = ix.bstart[base + blo]; pe = ix.bstart[base + min(blo + nbins, ix.nb)]; }
       else { const int e1 = blo + nbins - ix.nb; if (e1 <= 0) break; p = ix.bstart[base]; pe = ix.bstart[base + e1]; }
       for (p += sub; p < pe; p += 12) {  // two candidates in flight per lane
+        float4 tt[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) tt[u] = ld_slot<SMEM>(ix, p + 6 * u < pe ? p + 6 * u : p);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int pu = p + 6 * u;
-          const float4 t = ix.pts[pu < pe ? pu : p];
+          const float4 t = tt[u];
           const unsigned d = __float_as_uint(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z));
           const int j = slot_index(t.w);
           const bool fwd = j > c;
@@ -374,6 +400,13 @@ __device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, 
   } else {
     i3 = -1; pos3 = -1;
   }
+}
+
+template <bool SURF>
+__device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
+                                             float B2, float B3, int& i2, int& i3, int& pos2, int& pos3, float& slack) {
+  if (ix.sbase) az_scan_walk_t<SURF, true>(ix, s, ccr, w2, w3, fwdBound, nearf, B2, B3, i2, i3, pos2, pos3, slack);
+  else az_scan_walk_t<SURF, false>(ix, s, ccr, w2, w3, fwdBound, nearf, B2, B3, i2, i3, pos2, pos3, slack);
 }
 
 }  // namespace lins_dev

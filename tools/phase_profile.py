@@ -28,5 +28,6 @@ print("later passes, per search (lane-0 clocks): closest-point mean %.0f max %.0
     t[20]/max(t[10]-n*550,1), t[22], t[17]/max(its-n,1), t[16]/max(t[17],1), t[30]/max(t[11]-n*550,1), 100*t[31]/max(t[30],1)))
 c = max(t[36], 1)
 print("later-pass closest-point search, mean cycles: fetch+loads %.0f | setup+scan loop %.0f | arg-min %.0f | epilogue %.0f" % (t[32]/c, t[33]/c, t[34]/c, t[35]/c))
+print("later-pass closest-point search: candidates of the busiest lane %.1f, of all lanes %.1f" % (t[37]/c, t[38]/c))
 print("work lists per iteration: closest-point searches %.1f (ring-bins per search %.1f; first pass %.1f), walk searches %.1f (ring-bins per search %.1f; first pass %.1f)" % (
     t[10]/its, t[12]/max(t[10],1), t[14]/max(n,1)/550, t[11]/its, t[13]/max(t[11],1), t[15]/max(n,1)/550))
