@@ -2,9 +2,15 @@
 // Host side is plain C++ / CUDA runtime: no torch, no Eigen, no PCL in any signature.  There is NO CPU
 // fallback: every entry point fails with LINS_E_NODEVICE / LINS_E_CUDA when the device path is unavailable.
 #include <cuda_runtime.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
@@ -427,7 +433,62 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
 
 }  // namespace
 
+// Persistent host workers of a context (packing + staging of uploads): created on first use, parked on a condition
+// variable between uploads, so an upload does not pay for thread creation.
+class HostPool {
+ public:
+  ~HostPool() {
+    { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // run fn() on `n` threads in total (the caller is one of them) and wait for all of them
+  void run(int n, const std::function<void()>& fn) {
+    const int extra = std::max(0, n - 1);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      while ((int)th_.size() < extra) th_.emplace_back([this] { loop(); });
+      fn_ = &fn; want_ = extra; taken_ = 0; done_ = 0; ++gen_;
+    }
+    cv_.notify_all();
+    fn();
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return done_ == want_; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<void()>* fn = nullptr;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return stop_ || (gen_ != seen && taken_ < want_); });
+        if (stop_) return;
+        seen = gen_;
+        ++taken_;
+        fn = fn_;
+      }
+      (*fn)();
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        ++done_;
+      }
+      cv_done_.notify_one();
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_, cv_done_;
+  std::vector<std::thread> th_;
+  const std::function<void()>* fn_ = nullptr;
+  int want_ = 0, taken_ = 0, done_ = 0;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+};
+
 struct lins_ctx {
+  HostPool pool;
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -464,7 +525,21 @@ int fail(lins_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
     if (_e != cudaSuccess) return fail(ctx, LINS_E_CUDA, #call, _e); \
   } while (0)
 
+// pcl::PointXYZI (32 B) -> (x, y, z, intensity) (16 B).  The destination is pinned staging that the copy engine
+// reads next and the host never reads back: SSE2 (x86-64 baseline) with non-temporal stores.
 inline void pack_into(float4* dst, const lins_point* src, int n) {
+#if defined(__SSE2__)
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    for (int i = 0; i < n; ++i) {
+      const __m128 a = _mm_loadu_ps(&src[i].x);                         // x y z pad
+      const __m128 b = _mm_load_ss(&src[i].intensity);                  // i 0 0 0
+      const __m128 t = _mm_shuffle_ps(a, b, _MM_SHUFFLE(0, 0, 2, 2));   // z z i i
+      _mm_stream_ps(reinterpret_cast<float*>(dst + i), _mm_shuffle_ps(a, t, _MM_SHUFFLE(2, 0, 1, 0)));  // x y z i
+    }
+    _mm_sfence();
+    return;
+  }
+#endif
   for (int i = 0; i < n; ++i) dst[i] = make_float4(src[i].x, src[i].y, src[i].z, src[i].intensity);
 }
 
@@ -796,13 +871,14 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
         if (e != cudaSuccess) cuda_err.store((int)e);
       }
     };
+    // pack threads: LINS_PACK_THREADS when set (a job that runs several contexts / ranks per host divides the cores
+    // among them), else half the hardware threads, at most 32
     unsigned hw = std::thread::hardware_concurrency();
-    int nthr = (int)std::min<size_t>(std::min<unsigned>(hw ? hw / 2 : 4, 32), std::max<size_t>(slices.size(), 1));
+    int want = (int)std::min<unsigned>(hw ? hw / 2 : 4, 32);
+    if (const char* e = std::getenv("LINS_PACK_THREADS")) { const int v = std::atoi(e); if (v >= 1) want = std::min(v, 64); }
+    int nthr = (int)std::min<size_t>((size_t)want, std::max<size_t>(slices.size(), 1));
     if (nthr < 1) nthr = 1;
-    std::vector<std::thread> th;
-    for (int t = 1; t < nthr; ++t) th.emplace_back(worker);
-    worker();
-    for (auto& t : th) t.join();
+    ctx->pool.run(nthr, worker);
     if (cuda_err.load() != 0) return fail(ctx, LINS_E_CUDA, "H2D copy of a packed slice", (cudaError_t)cuda_err.load());
   }
   for (int k = 0; k < 4; ++k) std::memcpy(r.h_off.p + (size_t)k * (n + 1), offs[k], sizeof(int) * (n + 1));
