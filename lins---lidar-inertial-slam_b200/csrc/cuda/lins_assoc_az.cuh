@@ -140,16 +140,6 @@ __device__ __forceinline__ float search_slack(unsigned best_bits, unsigned secon
   return fminf(ds - db, gate * 0.99999f - db);                     // stays the winner, stays inside the gate
 }
 
-// warp arg-min of u64 keys with a payload, through the redux unit (two 32-bit reductions instead of 15 shuffles)
-__device__ __forceinline__ void warp_argmin(unsigned long long& k, int& payload) {
-  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)(k & 0xffffffffu);
-  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
-  const unsigned win = __ballot_sync(0xffffffffu, hi == mhi && lo == mlo);
-  payload = __shfl_sync(0xffffffffu, payload, __ffs(win) - 1);
-  k = ((unsigned long long)mhi << 32) | mlo;
-}
-
 // ---- phase P1 (one THREAD per query): azimuth, range, bound and window of the closest-point search ------------
 // qa = (azimuth, rho, -, outside bound B1); returns the packed window or -1 when the query cannot match anything
 __device__ __forceinline__ void az_polar(const float4 s, float4& qa) {
@@ -194,11 +184,6 @@ __device__ __forceinline__ int az_probe_window(const AzIndex& ix, const float4 q
 
 // ---- phase P2 (one WARP per query): exact 1-NN over all rings inside the window ---------------------------------
 // LPR lanes share one ring; two candidates per lane are in flight per trip (the scan is latency bound).
-// (best, second): the lane's smallest key and the distance bits of its runner-up
-__device__ __forceinline__ void take(unsigned long long k, int p, unsigned long long& best, unsigned& second, int& bpos) {
-  if (k < best) { second = (unsigned)(best >> 32); best = k; bpos = p; }
-  else { const unsigned d = (unsigned)(k >> 32); second = d < second ? d : second; }
-}
 // Branch-free bookkeeping of (best key, its slot, runner-up distance): a lone warp runs these scans with nothing to
 // hide latency behind, so the loop body is straight-line code with independent chains (four candidates per lane per
 // trip, reduced as a small tournament) instead of data-dependent branches.

@@ -334,16 +334,6 @@ __global__ void __launch_bounds__(kJacThreads, kJacMinBlocks) lins_jacobian_kern
   }
 }
 
-// Pack pcl::PointXYZI (32 B AoS) -> float4 (x, y, z, intensity) on device, for clouds uploaded raw.
-__global__ void lins_pack_points_kernel(const lins_point* __restrict__ in, float4* __restrict__ out, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * (size_t)i);
-    const float b = __ldg(reinterpret_cast<const float*>(in) + 8 * (size_t)i + 4);
-    out[i] = make_float4(a.x, a.y, a.z, b);
-  }
-}
-
 // F1: transformToEnd (StateEstimator.hpp:1083-1101) of a packed cloud, in place on device.
 __global__ void lins_transform_to_end_kernel(float4* __restrict__ pts, int n, const double* __restrict__ lin,
                                              double scan_period) {

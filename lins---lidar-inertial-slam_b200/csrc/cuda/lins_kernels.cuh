@@ -146,16 +146,6 @@ struct Smem {
   } while (0)
 
 // ---------------------------------------------------------------------------------------------------------
-// per-iteration constants (thread 0)
-__device__ void compute_iter_consts(Smem& sm) {
-  q4 q; q.x = sm.lin[6]; q.y = sm.lin[7]; q.z = sm.lin[8]; q.w = sm.lin[9];
-  d3 phi = Quat2axis(q);
-  sm.phi[0] = phi.x; sm.phi[1] = phi.y; sm.phi[2] = phi.z;
-  m3 R = qtoR(q);
-  m3 Ri = Rinvleft(mk3(-phi.x, -phi.y, -phi.z));
-  for (int i = 0; i < 9; ++i) { sm.R[i] = R.m[i]; sm.Rinv[i] = Ri.m[i]; }
-}
-
 // A2 transformToStart (StateEstimator.hpp:1066-1080) -------------------------------------------------------
 __device__ __forceinline__ float4 transform_to_start(const float4 p, const Smem& sm, double scan_period) {
   float fi = p.w - (float)((int)p.w);
@@ -417,92 +407,7 @@ __device__ void block_reduce_acc(Smem& sm, double* acc, int cs, int cc, bool fin
   __syncthreads();
 }
 
-// N x N (N <= 32) LU with partial pivoting by one warp; S row-major (destroyed), B = N x nrhs row-major
-// (-> solution).  Pivot choice = first maximum of |column| from the diagonal down (same as a sequential scan).
-template <int N>
-__device__ bool warp_lu_solve(double* S, double* B, int nrhs) {
-  const int lane = threadIdx.x & 31;
-  bool ok = true;
-  for (int k = 0; k < N; ++k) {
-    double v = -1.0;
-    if (lane >= k && lane < N) {
-      v = fabs(S[lane * N + k]);
-      if (v != v) v = (lane == k) ? __longlong_as_double(0x7ff8000000000000ll) : -1.0;
-    }
-    // NaN on the diagonal poisons the step (a sequential scan would keep best = NaN)
-    unsigned nanmask = __ballot_sync(0xffffffffu, v != v);
-    int piv = lane;
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      double ov = __shfl_xor_sync(0xffffffffu, v, m);
-      int op = __shfl_xor_sync(0xffffffffu, piv, m);
-      if (ov > v || (ov == v && op < piv)) { v = ov; piv = op; }
-    }
-    if (nanmask != 0u || !(v > 0.0)) { ok = false; break; }
-    if (piv != k) {
-      if (lane < N) { double t = S[k * N + lane]; S[k * N + lane] = S[piv * N + lane]; S[piv * N + lane] = t; }
-      for (int j = lane; j < nrhs; j += 32) { double t = B[k * nrhs + j]; B[k * nrhs + j] = B[piv * nrhs + j]; B[piv * nrhs + j] = t; }
-    }
-    __syncwarp();
-    const double inv = 1.0 / S[k * N + k];
-    if (lane > k && lane < N) {
-      const double f = S[lane * N + k] * inv;
-      if (f != 0.0) {
-        for (int j = k + 1; j < N; ++j) S[lane * N + j] -= f * S[k * N + j];
-        for (int j = 0; j < nrhs; ++j) B[lane * nrhs + j] -= f * B[k * nrhs + j];
-      }
-    }
-    __syncwarp();
-  }
-  if (!ok) return false;
-  for (int k = N - 1; k >= 0; --k) {
-    const double inv = 1.0 / S[k * N + k];
-    for (int j = lane; j < nrhs; j += 32) {
-      double s = B[k * nrhs + j];
-      for (int c = k + 1; c < N; ++c) s -= S[k * N + c] * B[c * nrhs + j];
-      B[k * nrhs + j] = s * inv;
-    }
-    __syncwarp();
-  }
-  return true;
-}
-
 __device__ __forceinline__ int col6(int a) { return a < 3 ? a : a + 3; }  // {0,1,2,6,7,8}
-
-// Build A6 = T Ag T^T (information matrix on the 6 structural columns) from the reduced accumulators.
-// T = blockdiag(I3, Rinv^T).  36 threads.
-__device__ void build_A6(Smem& sm) {
-  const int t = threadIdx.x;
-  if (t < 36) {
-    const int a = t / 6, c = t % 6;
-    // Ag full from packed upper triangle
-    auto Ag = [&](int i, int j) -> double {
-      if (i > j) { int tmp = i; i = j; j = tmp; }
-      int idx = i * 6 - (i * (i - 1)) / 2 + (j - i);
-      return sm.acc[idx];
-    };
-    auto T = [&](int i, int j) -> double {
-      if (i < 3 || j < 3) return (i == j) ? 1.0 : 0.0;
-      return sm.Rinv[(j - 3) * 3 + (i - 3)];  // (Rinv^T)[i-3][j-3]
-    };
-    double s = 0;
-    for (int i = 0; i < 6; ++i) {
-      double ti = T(a, i);
-      if (ti == 0.0) continue;
-      double u = 0;
-      for (int j = 0; j < 6; ++j) u += Ag(i, j) * T(c, j);
-      s += ti * u;
-    }
-    sm.A6[t] = s;
-  }
-  if (t >= 64 && t < 70) {
-    const int a = t - 64;
-    double s = 0;
-    if (a < 3) s = sm.acc[21 + a];
-    else for (int i = 0; i < 3; ++i) s += sm.Rinv[i * 3 + (a - 3)] * sm.acc[24 + i];
-    sm.y6[a] = s;  // b_h (b + A d added later)
-  }
-}
 
 // M = A6 P_cc + sig2 I6: the 6x6 system of the gain in push-through form.  With H = H6 E_c^T (only the 6
 // structural columns c = {0,1,2,6,7,8} are non-zero) and R = sig2 I:
@@ -518,21 +423,6 @@ __device__ void form_M6(Smem& sm, double sig2, int idx, int stride) {
   }
 }
 
-// filterState (-) linState  (KalmanFilter.hpp:84-94), thread 0
-__device__ void box_minus(Smem& sm) {
-  const double* f = sm.prior; const double* l = sm.lin;
-  for (int i = 0; i < 3; ++i) {
-    sm.dvec[0 + i] = f[0 + i] - l[0 + i];
-    sm.dvec[3 + i] = f[3 + i] - l[3 + i];
-    sm.dvec[9 + i] = f[10 + i] - l[10 + i];
-    sm.dvec[12 + i] = f[13 + i] - l[13 + i];
-    sm.dvec[15 + i] = f[16 + i] - l[16 + i];
-  }
-  q4 ql; ql.x = l[6]; ql.y = l[7]; ql.z = l[8]; ql.w = l[9];
-  q4 qf; qf.x = f[6]; qf.y = f[7]; qf.z = f[8]; qf.w = f[9];
-  d3 da = Quat2axis(qmul(qinverse(ql), qf));
-  sm.dvec[6] = da.x; sm.dvec[7] = da.y; sm.dvec[8] = da.z;
-}
 // linState (+) updateVec (KalmanFilter.hpp:71-81), thread 0
 __device__ void box_plus(Smem& sm) {
   double* l = sm.lin; const double* u = sm.upd;
@@ -552,9 +442,9 @@ __device__ void box_plus(Smem& sm) {
 
 // N x N LU with partial pivoting, one COLUMN per lane held in registers: lanes [0, N) own the columns of S
 // (row-major in shared memory), lanes [N, N + nrhs) the right-hand sides B (N x nrhs row-major, overwritten by
-// the solution).  Same pivot rule (first maximum of |column| from the diagonal down; a NaN on the diagonal
-// poisons the step) and the same multiply / subtract sequence per entry as warp_lu_solve, at a third of its
-// latency: no shared-memory round trips, one division per step.  nrhs <= 32 - N.
+// the solution).  Pivot = first maximum of |column| from the diagonal down (what a sequential scan picks; a NaN
+// on the diagonal poisons the step); one division per step; only the initial loads and the final stores touch
+// shared memory.  nrhs <= 32 - N.
 template <int N>
 __device__ bool warp_lu_cols(const double* S, double* B, int nrhs) {
   const int lane = threadIdx.x & 31;
