@@ -167,6 +167,40 @@ int lins_gpu_batch_results_device(lins_ctx* ctx, void** dev_ptr, int* n_scans);
    point. Used for the HBM-roofline measurement; results land in an internal n x 29 accumulator array. */
 int lins_gpu_batch_jacobian_pass(lins_ctx* ctx, double* accum_out /*n x 29 or NULL*/);
 
+/* ---- row F2: the mapping node's scan-to-map refinement -------------------------------------
+   lins/src/lidar_mapping_node.cpp: scan2MapOptimization :1635-1652, cornerOptimization :1351-1461,
+   surfOptimization :1463-1524, LMOptimization :1526-1633, pointAssociateToMap :594-608.
+   All point clouds are in the mapping node's frame convention (the YZX clouds the estimator publishes);
+   transform = transformTobeMapped = (rx, ry, rz, tx, ty, tz), f32 like the reference. */
+#define LINS_MAP_MAX_ITER 10
+typedef struct lins_map_report {
+  int32_t iters;       /* LM iterations executed (<= 10) */
+  int32_t converged;   /* deltaR < 0.05 deg && deltaT < 0.05 cm reached (:1628) */
+  int32_t degenerate;  /* isDegenerate of iteration 0 (:1606-1617) */
+  int32_t skipped;     /* map too small: cornerFromMapDSNum <= 10 || surfFromMapDSNum <= 100 (:1636) */
+  int32_t n_sel[LINS_MAP_MAX_ITER];   /* laserCloudSelNum per iteration (< 50 => that LM step is skipped, :1535) */
+  float delta_r[LINS_MAP_MAX_ITER];   /* deg */
+  float delta_t[LINS_MAP_MAX_ITER];   /* cm */
+} lins_map_report;
+
+/* ≙ kdtreeCornerFromMap->setInputCloud(laserCloudCornerFromMapDS), kdtreeSurfFromMap->setInputCloud(...) (:1637-1638):
+   uploads both map clouds and builds the device search structure. */
+int lins_gpu_map_set(lins_ctx* ctx, const lins_point* corner_from_map, int n_corner, const lins_point* surf_from_map,
+                     int n_surf);
+/* ≙ the iteration loop of scan2MapOptimization (:1640-1648): up to 10 x (cornerOptimization, surfOptimization,
+   LMOptimization) against the map set by lins_gpu_map_set; 5-NN search, line / plane fits, coefficients and the
+   A^T A / A^T B reduction on the device, the 6x6 step on the host.  transform_io: transformTobeMapped in / out.
+   (transformUpdate, :538-577, blends IMU roll / pitch afterwards and stays with the caller.) */
+int lins_gpu_scan2map(lins_ctx* ctx, const lins_point* corner_last, int n_corner, const lins_point* surf_last, int n_surf,
+                      float* transform_io /*6*/, lins_map_report* rep);
+/* ≙ one cornerOptimization + surfOptimization pass at `transform`, dense per-point outputs (any pointer may be NULL):
+   knn = pointSearchInd (5 per point, ascending distance, -1 = fewer than 5 map points), coeff = (s*la, s*lb, s*lc,
+   s*ld2) resp. (s*pa, s*pb, s*pc, s*pd2), mask = the point was pushed to laserCloudOri (s > 0.1). */
+int lins_gpu_map_associate(lins_ctx* ctx, const lins_point* corner_last, int n_corner, const lins_point* surf_last,
+                           int n_surf, const float* transform /*6*/, int32_t* corner_knn /*5*n_corner*/,
+                           int32_t* surf_knn /*5*n_surf*/, float* corner_coeff /*4*n_corner*/, float* surf_coeff /*4*n_surf*/,
+                           uint8_t* corner_mask, uint8_t* surf_mask);
+
 /* block until everything queued on the ctx stream has finished */
 int lins_gpu_sync(lins_ctx* ctx);
 

@@ -54,6 +54,12 @@ class LinsReport(C.Structure):
     ]
 
 
+class LinsMapReport(C.Structure):
+    """lins_map_report (include/lins_gpu.h, row F2)."""
+    _fields_ = [("iters", C.c_int32), ("converged", C.c_int32), ("degenerate", C.c_int32), ("skipped", C.c_int32),
+                ("n_sel", C.c_int32 * 10), ("delta_r", C.c_float * 10), ("delta_t", C.c_float * 10)]
+
+
 class LinsScanResult(C.Structure):
     _fields_ = [
         ("scan_id", C.c_int32),

@@ -243,3 +243,78 @@ void lins_oracle_measurement_rows(const lins_params* p, const double* lin_state,
 }
 
 }  // extern "C"
+
+// ---- row F2: mapping-node scan-to-map refinement (lins_map_oracle.hpp) -----------------------------------------------
+#include "lins_map_oracle.hpp"
+
+namespace {
+std::vector<lins_map_oracle::P3> to_p3(const lins_point* p, int n) {
+  std::vector<lins_map_oracle::P3> v(n);
+  for (int i = 0; i < n; ++i) v[i] = lins_map_oracle::P3{p[i].x, p[i].y, p[i].z, p[i].intensity};
+  return v;
+}
+}  // namespace
+
+extern "C" {
+
+void* lins_map_oracle_create() { return new lins_map_oracle::Mapper(); }
+void lins_map_oracle_destroy(void* h) { delete static_cast<lins_map_oracle::Mapper*>(h); }
+int lins_map_oracle_set_map(void* h, const lins_point* corner, int nc, const lins_point* surf, int ns) {
+  static_cast<lins_map_oracle::Mapper*>(h)->setMap(corner, nc, surf, ns);
+  return 0;
+}
+int lins_map_oracle_associate(void* h, const lins_point* corner, int nc, const lins_point* surf, int ns, const float* T,
+                              int32_t* cknn, int32_t* sknn, float* ccoeff, float* scoeff, uint8_t* cmask, uint8_t* smask) {
+  lins_map_oracle::Transform t;
+  std::memcpy(t.v, T, sizeof(t.v));
+  static_cast<lins_map_oracle::Mapper*>(h)->associate(to_p3(corner, nc), to_p3(surf, ns), t, cknn, sknn, ccoeff, scoeff, cmask, smask,
+                                                      nullptr, nullptr);
+  return 0;
+}
+int lins_map_oracle_scan2map(void* h, const lins_point* corner, int nc, const lins_point* surf, int ns, float* T_io,
+                             lins_map_report* rep) {
+  lins_map_oracle::Transform t;
+  std::memcpy(t.v, T_io, sizeof(t.v));
+  lins_map_oracle::Report r;
+  static_cast<lins_map_oracle::Mapper*>(h)->scan2map(to_p3(corner, nc), to_p3(surf, ns), t, r);
+  std::memcpy(T_io, t.v, sizeof(t.v));
+  if (rep) {
+    std::memset(rep, 0, sizeof(*rep));
+    rep->iters = r.iters; rep->converged = r.converged; rep->degenerate = r.degenerate; rep->skipped = r.skipped;
+    for (int i = 0; i < (int)r.n_sel.size() && i < LINS_MAP_MAX_ITER; ++i) {
+      rep->n_sel[i] = r.n_sel[i]; rep->delta_r[i] = r.delta_r[i]; rep->delta_t[i] = r.delta_t[i];
+    }
+  }
+  return 0;
+}
+// the 6x6 step alone (what the product's host side does after the device reduction)
+int lins_map_oracle_lm_solve(void* h, const float* AtA, const float* AtB, int iter, float* T_io, float* X_out, int* degenerate) {
+  lins_map_oracle::Mapper* m = static_cast<lins_map_oracle::Mapper*>(h);
+  lins_map_oracle::Transform t;
+  std::memcpy(t.v, T_io, sizeof(t.v));
+  lins_map_oracle::Report r;
+  float X[6];
+  const bool conv = m->lm_solve(AtA, AtB, iter, t, r, X);
+  std::memcpy(T_io, t.v, sizeof(t.v));
+  if (X_out) std::memcpy(X_out, X, sizeof(X));
+  if (degenerate) *degenerate = r.degenerate;
+  return conv ? 1 : 0;
+}
+// numerical kernels, for pinning against the real OpenCV (tests/test_map_oracle_cpu.py)
+void lins_map_oracle_eigen(const float* A, int n, float* W, float* V) {
+  std::vector<float> a(A, A + (size_t)n * n);
+  lins_map_oracle::jacobi_eigen(a.data(), n, W, V);
+}
+int lins_map_oracle_qr_solve(const float* A, int m, int n, const float* b, float* x) {
+  std::vector<float> a(A, A + (size_t)m * n), bb(b, b + m);
+  const bool ok = lins_map_oracle::qr_solve(a.data(), m, n, bb.data());
+  for (int i = 0; i < n; ++i) x[i] = ok ? bb[i] : 0.f;
+  return ok ? 1 : 0;
+}
+int lins_map_oracle_lu_invert(const float* A, int n, float* Ainv) {
+  std::vector<float> a(A, A + (size_t)n * n);
+  return lins_map_oracle::lu_invert(a.data(), n, Ainv) ? 1 : 0;
+}
+void lins_map_oracle_gemm(const float* A, const float* B, float* C, int m, int k, int n) { lins_map_oracle::gemm_f32(A, B, C, m, k, n); }
+
+}  // extern "C"

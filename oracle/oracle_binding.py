@@ -53,6 +53,17 @@ def lib():
         L.lins_oracle_boxminus.argtypes = [vp, vp, vp]
         L.lins_oracle_transform.argtypes = [C.POINTER(LinsParams), vp, C.c_int, vp, C.c_int, vp]
         L.lins_oracle_measurement_rows.argtypes = [C.POINTER(LinsParams), vp, vp, vp, C.c_int, vp, vp]
+        # row F2 (mapping refinement)
+        L.lins_map_oracle_create.restype = vp
+        L.lins_map_oracle_destroy.argtypes = [vp]
+        L.lins_map_oracle_set_map.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+        L.lins_map_oracle_associate.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp] + [vp] * 6
+        L.lins_map_oracle_scan2map.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.POINTER(_defs.LinsMapReport)]
+        L.lins_map_oracle_lm_solve.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.POINTER(C.c_int)]
+        L.lins_map_oracle_eigen.argtypes = [vp, C.c_int, vp, vp]
+        L.lins_map_oracle_qr_solve.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+        L.lins_map_oracle_lu_invert.argtypes = [vp, C.c_int, vp]
+        L.lins_map_oracle_gemm.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int]
         _LIB = L
     return _LIB
 
@@ -149,3 +160,79 @@ def ieskf_batch(params, batch, first=0, count=None, form=FORM_B, use_kdtree=True
     L.lins_oracle_ieskf_batch(C.byref(params), C.byref(d), first, count, form, int(use_kdtree), threads, ptr(so), ptr(co),
                               ptr(res), C.byref(sec), C.byref(its))
     return so, co, res, sec.value, its.value
+
+
+# ---- row F2: mapping-node scan-to-map refinement (oracle/lins_map_oracle.hpp) ------------------------------------------
+class MapOracle:
+    """CPU restatement of scan2MapOptimization (lidar_mapping_node.cpp:1635-1652)."""
+
+    def __init__(self):
+        self._h = lib().lins_map_oracle_create()
+
+    def close(self):
+        if self._h:
+            lib().lins_map_oracle_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_map(self, corner_map, surf_map):
+        c, s = as_points(corner_map), as_points(surf_map)
+        lib().lins_map_oracle_set_map(self._h, ptr(c), len(c), ptr(s), len(s))
+
+    def associate(self, corner_last, surf_last, transform):
+        c, s = as_points(corner_last), as_points(surf_last)
+        t = np.ascontiguousarray(transform, np.float32)
+        out = dict(corner_knn=np.zeros((len(c), 5), np.int32), surf_knn=np.zeros((len(s), 5), np.int32),
+                   corner_coeff=np.zeros((len(c), 4), np.float32), surf_coeff=np.zeros((len(s), 4), np.float32),
+                   corner_mask=np.zeros(len(c), np.uint8), surf_mask=np.zeros(len(s), np.uint8))
+        lib().lins_map_oracle_associate(self._h, ptr(c), len(c), ptr(s), len(s), ptr(t), ptr(out["corner_knn"]), ptr(out["surf_knn"]),
+                                        ptr(out["corner_coeff"]), ptr(out["surf_coeff"]), ptr(out["corner_mask"]), ptr(out["surf_mask"]))
+        return out
+
+    def scan2map(self, corner_last, surf_last, transform):
+        c, s = as_points(corner_last), as_points(surf_last)
+        t = np.array(transform, np.float32).copy()
+        rep = _defs.LinsMapReport()
+        lib().lins_map_oracle_scan2map(self._h, ptr(c), len(c), ptr(s), len(s), ptr(t), C.byref(rep))
+        return t, rep
+
+    def lm_solve(self, AtA, AtB, it, transform):
+        a, b = np.ascontiguousarray(AtA, np.float32), np.ascontiguousarray(AtB, np.float32)
+        t = np.array(transform, np.float32).copy()
+        x = np.zeros(6, np.float32)
+        deg = C.c_int(0)
+        conv = lib().lins_map_oracle_lm_solve(self._h, ptr(a), ptr(b), it, ptr(t), ptr(x), C.byref(deg))
+        return t, x, bool(conv), bool(deg.value)
+
+
+def cv_eigen(A):
+    A = np.ascontiguousarray(A, np.float32); n = A.shape[0]
+    W, V = np.zeros(n, np.float32), np.zeros((n, n), np.float32)
+    lib().lins_map_oracle_eigen(ptr(A), n, ptr(W), ptr(V))
+    return W, V
+
+
+def cv_qr_solve(A, b):
+    A = np.ascontiguousarray(A, np.float32); b = np.ascontiguousarray(b, np.float32).reshape(-1)
+    x = np.zeros(A.shape[1], np.float32)
+    ok = lib().lins_map_oracle_qr_solve(ptr(A), A.shape[0], A.shape[1], ptr(b), ptr(x))
+    return bool(ok), x
+
+
+def cv_lu_invert(A):
+    A = np.ascontiguousarray(A, np.float32); n = A.shape[0]
+    Ai = np.zeros((n, n), np.float32)
+    ok = lib().lins_map_oracle_lu_invert(ptr(A), n, ptr(Ai))
+    return bool(ok), Ai
+
+
+def cv_gemm(A, B):
+    A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32)
+    Cm = np.zeros((A.shape[0], B.shape[1]), np.float32)
+    lib().lins_map_oracle_gemm(ptr(A), ptr(B), ptr(Cm), A.shape[0], A.shape[1], B.shape[1])
+    return Cm
