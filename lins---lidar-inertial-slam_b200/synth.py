@@ -156,3 +156,36 @@ def run_sequence(config="config3", seed=1, n_scans=12, device=0, **overrides):
                     status=ints(3, ns), global_est=arr(2, ns * 7).reshape(-1, 7), global_true=arr(3, ns * 7).reshape(-1, 7))
     finally:
         L.lins_seq_destroy(h)
+
+
+# ---- row F2: scan-to-map units (tools/synth/lins_synth.cpp: lins_synth_map_unit_create) -------------------------------
+class MapUnit:
+    """One scan2MapOptimization input: map clouds, the newest scan's (down-sampled) features, true / guessed transform."""
+
+    def __init__(self, corner_map, surf_map, corner_last, surf_last, truth, guess):
+        self.corner_map, self.surf_map, self.corner_last, self.surf_last = corner_map, surf_map, corner_last, surf_last
+        self.truth, self.guess = truth, guess
+
+
+def generate_map_unit(config="config3", seed=1, n_keyframes=20, sigma_t=0.1, sigma_r=0.01, **overrides):
+    L = lib()
+    L.lins_synth_map_unit_create.restype = C.c_void_p
+    L.lins_synth_map_unit_create.argtypes = [C.POINTER(SynthCfg), C.c_uint64, C.c_int, C.c_double, C.c_double]
+    L.lins_synth_map_unit_destroy.argtypes = [C.c_void_p]
+    L.lins_synth_map_unit_cloud.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.lins_synth_map_unit_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    kw = dict(CONFIGS[config])
+    kw.update(overrides)
+    cfg = SynthCfg(**kw)
+    h = L.lins_synth_map_unit_create(C.byref(cfg), seed, n_keyframes, sigma_t, sigma_r)
+    try:
+        clouds = []
+        for which in range(4):
+            p = C.c_void_p()
+            n = L.lins_synth_map_unit_cloud(h, which, C.byref(p))
+            clouds.append(_copy(p.value, n, POINT_DTYPE))
+        truth, guess = np.zeros(6, np.float32), np.zeros(6, np.float32)
+        L.lins_synth_map_unit_transforms(h, truth.ctypes.data_as(C.c_void_p), guess.ctypes.data_as(C.c_void_p))
+        return MapUnit(*clouds, truth, guess)
+    finally:
+        L.lins_synth_map_unit_destroy(h)

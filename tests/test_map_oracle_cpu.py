@@ -66,3 +66,78 @@ def test_lu_invert_and_small_gemm_are_cv_bit_for_bit():
         M = rng.standard_normal((6, 6)).astype(f32) * f32(rng.uniform(0.1, 10))
         ok, Mi = ob.cv_lu_invert(M)
         assert ok and np.array_equal(cv2.invert(M, flags=cv2.DECOMP_LU)[1], Mi), t
+
+
+# ---- the whole refinement against the fixture made with the real OpenCV (tests/golden/make_map_golden.py) -----------
+import os  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "map_unit.npz")
+
+
+def _gold():
+    return np.load(GOLD)
+
+
+def test_oracle_pass_matches_cv2_golden_bit_for_bit():
+    """Iteration 0 of cornerOptimization / surfOptimization: 5-NN indices, coefficients and masks are pure f32
+    arithmetic + cv::eigen / cv::solve, so the oracle must reproduce the cv2-made fixture exactly."""
+    g = _gold()
+    m = ob.MapOracle()
+    m.set_map(g["corner_map"], g["surf_map"])
+    out = m.associate(g["corner_last"], g["surf_last"], g["guess"])
+    for k in ("corner_knn", "surf_knn", "corner_mask", "surf_mask"):
+        assert np.array_equal(out[k], g["it0_" + k]), k
+    for k in ("corner_coeff", "surf_coeff"):
+        assert np.array_equal(out[k].view(np.uint32), g["it0_" + k].view(np.uint32)), k
+    assert out["corner_mask"].sum() > 50 and out["surf_mask"].sum() > 1000
+
+
+def test_oracle_scan2map_matches_cv2_golden():
+    """Whole loop.  matAtA = matAt * matA goes through cv::gemm, whose summation order depends on the OpenCV build
+    (BLAS here); the oracle accumulates in f64, so the transform is compared at 1e-5 (rad / m), the rest exactly."""
+    g = _gold()
+    m = ob.MapOracle()
+    m.set_map(g["corner_map"], g["surf_map"])
+    T, rep = m.scan2map(g["corner_last"], g["surf_last"], g["guess"])
+    assert rep.iters == int(g["iters"]) and rep.converged == int(g["converged"]) and rep.degenerate == int(g["degenerate"])
+    assert list(rep.n_sel)[:rep.iters] == list(g["n_sel"])
+    assert np.abs(T - g["T_out"]).max() < 1e-5
+    assert np.allclose(np.array(list(rep.delta_r)[:rep.iters]), g["delta_r"], rtol=2e-3, atol=1e-5)
+    # and the refinement does refine: translation error shrinks by > 5x on this unit
+    assert np.abs(T[3:] - g["truth"][3:]).max() < 0.2 * np.abs(g["guess"][3:] - g["truth"][3:]).max()
+
+
+def test_lm_step_on_cv2_normal_equations_is_exact():
+    """Given the fixture's own matAtA / matAtB (made by cv2.gemm), the 6x6 step (QR solve, eigen-degeneracy test,
+    update, deltaR / deltaT) is bit-exact."""
+    g = _gold()
+    m = ob.MapOracle()
+    T = g["guess"].astype(np.float32).copy()
+    m2 = ob.MapOracle()
+    for it in range(int(g["iters"])):
+        A, b = g["AtA"][it], g["AtB"][it]
+        T2, x, conv, deg = m2.lm_solve(A, b, it, T)
+        ok, xr = cv2.solve(A, b.reshape(6, 1), flags=cv2.DECOMP_QR)
+        assert np.array_equal(x, xr.ravel()) and not deg
+        assert abs(float(np.sqrt(sum((float(np.float32(v * np.float32(57.29578))) ** 2 for v in x[:3])))) - float(g["delta_r"][it])) < 1e-6
+        T = T2
+
+
+def test_map_edge_cases():
+    g = _gold()
+    m = ob.MapOracle()
+    # map too small: scan2MapOptimization does nothing (:1636)
+    m.set_map(g["corner_map"][:10], g["surf_map"])
+    T, rep = m.scan2map(g["corner_last"], g["surf_last"], g["guess"])
+    assert rep.skipped == 1 and rep.iters == 0 and np.array_equal(T, g["guess"])
+    # fewer than 50 selected points: LMOptimization returns false every time, 10 passes, transform untouched (:1535)
+    m.set_map(g["corner_map"], g["surf_map"])
+    T, rep = m.scan2map(g["corner_last"][:20], g["surf_last"][:20], g["guess"])
+    assert rep.iters == 10 and rep.converged == 0 and np.array_equal(T, g["guess"]) and max(list(rep.n_sel)) < 50
+    # fewer than 5 map points around: indices -1, nothing selected
+    far = g["surf_last"][:4].copy(); far["x"] += 500
+    out = m.associate(g["corner_last"][:0], far, g["guess"])
+    assert out["surf_mask"].sum() == 0 and (out["surf_knn"] >= 0).all()  # the map has >= 5 points, they are just > 1 m away
+    m.set_map(g["corner_map"], g["surf_map"][:3])
+    out = m.associate(g["corner_last"][:0], g["surf_last"][:4], g["guess"])
+    assert (out["surf_knn"][:, 3:] == -1).all() and out["surf_mask"].sum() == 0

@@ -348,4 +348,100 @@ void lins_synth_batch_new_less(void* h, int which, const lins_point** pts, const
   else { *pts = b->newCornerLessSharp.data(); *off = b->newCornerLessSharpOff.data(); }
 }
 
+
+// ---- row F2: one scan-to-map unit (what scan2MapOptimization sees, lidar_mapping_node.cpp:1635-1652) --------------------
+// K key-frames along a straight-ish drive through the seeded world: every key-frame's less-sharp corners and
+// less-flat surfs + outliers, moved to the map frame with its (slightly noisy) key pose, YZX axis order like the
+// clouds the estimator publishes (StateEstimator.hpp:1125-1150), voxel down-sampled with the mapping node's leaves
+// (0.2 m corners, 0.4 m surfs) -> laserCloudCornerFromMapDS / laserCloudSurfFromMapDS.  The newest scan's features
+// (down-sampled the same way, its own frame) are the queries; `truth` is its pose as transformTobeMapped
+// (rx, ry, rz, tx, ty, tz of pointAssociateToMap, :594-608), `guess` = truth + the odometry error to be refined.
+struct MapUnit {
+  std::vector<lins_point> cornerMap, surfMap, cornerLast, surfLast;
+  float truth[6], guess[6];
+};
+
+static lins_point yzx(const lins_point& p) { return makePoint(p.y, p.z, p.x, p.intensity); }
+static void euler_of(const M3D& Rw, const V3D& pw, float out[6]) {
+  // camera-convention rotation: Rc = P Rw P^T with P = (x,y,z) -> (y,z,x);  Rc = Ry(ry) Rx(rx) Rz(rz)
+  const int perm[3] = {1, 2, 0};
+  double Rc[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rc[i][j] = Rw(perm[i], perm[j]);
+  out[0] = (float)std::asin(-Rc[1][2]);
+  out[1] = (float)std::atan2(Rc[0][2], Rc[2][2]);
+  out[2] = (float)std::atan2(Rc[1][0], Rc[1][1]);
+  out[3] = (float)pw.y(); out[4] = (float)pw.z(); out[5] = (float)pw.x();
+}
+
+void* lins_synth_map_unit_create(const lins_synth_cfg* cfg, uint64_t seed, int n_keyframes, double sigma_t, double sigma_r) {
+  MapUnit* u = new MapUnit();
+  Rng rng(seed);
+  LidarModel lm = cfg->lidar == 1 ? LidarModel::dense64() : LidarModel::vlp16();
+  World w = make_world(rng, cfg->world);
+  Pose T;
+  double yaw = rng.uni(-M_PI, M_PI);
+  T.p = V3D(rng.uni(-3, 3), rng.uni(-3, 3), rng.uni(1.3, 1.7));
+  ImageProjection ip(lm);
+  FeatureExtractor fe(lm);
+  Cloud cornerAcc, surfAcc;
+  Twist still{V3D(0, 0, 0), V3D(0, 0, 0)};
+  for (int k = 0; k <= n_keyframes; ++k) {
+    T.R = math_utils::rpy2Quat(V3D(rng.uni(-0.02, 0.02), rng.uni(-0.02, 0.02), yaw)).toRotationMatrix();
+    Cloud raw;
+    simulate_scan(w, lm, T, still, cfg->range_noise, rng, raw);
+    ip.process(raw);
+    ScanFeatures f;
+    fe.run(ip.segmentedCloud, ip.segMsg, f);
+    if (k < n_keyframes) {  // a key-frame of the map: its pose is known up to the back-end's residual error
+      Pose Tk = T;
+      Tk.p = Tk.p + V3D(5e-3 * rng.gauss(), 5e-3 * rng.gauss(), 5e-3 * rng.gauss());
+      Tk.R = Tk.R * math_utils::axis2Quat(V3D(3e-4 * rng.gauss(), 3e-4 * rng.gauss(), 3e-4 * rng.gauss())).toRotationMatrix();
+      auto to_map = [&](const Cloud& c, Cloud& acc) {
+        for (const auto& p : c.points) {
+          V3D q = Tk.R * V3D(p.x, p.y, p.z) + Tk.p;
+          acc.push_back(makePoint((float)q.y(), (float)q.z(), (float)q.x(), p.intensity));
+        }
+      };
+      to_map(f.cornerPointsLessSharp, cornerAcc);
+      to_map(f.surfPointsLessFlat, surfAcc);
+      to_map(ip.outlierCloud, surfAcc);
+      // drive on: 0.8 .. 1.6 m forward, gentle heading change
+      yaw += rng.uni(-0.5, 0.5) * cfg->w_max;
+      const double step = rng.uni(0.8, 1.6);
+      T.p = T.p + V3D(step * std::cos(yaw), step * std::sin(yaw), 0.0);
+    } else {  // the newest scan: the queries
+      Cloud c, s, cds, sds;
+      for (const auto& p : f.cornerPointsLessSharp.points) c.push_back(yzx(p));
+      for (const auto& p : f.surfPointsLessFlat.points) s.push_back(yzx(p));
+      for (const auto& p : ip.outlierCloud.points) s.push_back(yzx(p));
+      VoxelGrid vc, vs;
+      vc.setLeafSize(0.2f, 0.2f, 0.2f); vs.setLeafSize(0.4f, 0.4f, 0.4f);
+      vc.filter(c, cds); vs.filter(s, sds);
+      u->cornerLast = cds.points; u->surfLast = sds.points;
+      euler_of(T.R, T.p, u->truth);
+      for (int i = 0; i < 3; ++i) u->guess[i] = u->truth[i] + (float)(sigma_r * rng.gauss());
+      for (int i = 3; i < 6; ++i) u->guess[i] = u->truth[i] + (float)(sigma_t * rng.gauss());
+    }
+  }
+  Cloud cds, sds;
+  VoxelGrid vc, vs;
+  vc.setLeafSize(0.2f, 0.2f, 0.2f); vs.setLeafSize(0.4f, 0.4f, 0.4f);
+  vc.filter(cornerAcc, cds); vs.filter(surfAcc, sds);
+  u->cornerMap = cds.points; u->surfMap = sds.points;
+  return u;
+}
+void lins_synth_map_unit_destroy(void* h) { delete static_cast<MapUnit*>(h); }
+// which: 0 corner map, 1 surf map, 2 corner last, 3 surf last
+int lins_synth_map_unit_cloud(void* h, int which, const lins_point** pts) {
+  MapUnit* u = static_cast<MapUnit*>(h);
+  const std::vector<lins_point>* v = which == 0 ? &u->cornerMap : which == 1 ? &u->surfMap : which == 2 ? &u->cornerLast : &u->surfLast;
+  *pts = v->data();
+  return (int)v->size();
+}
+void lins_synth_map_unit_transforms(void* h, float* truth, float* guess) {
+  MapUnit* u = static_cast<MapUnit*>(h);
+  std::memcpy(truth, u->truth, sizeof(u->truth));
+  std::memcpy(guess, u->guess, sizeof(u->guess));
+}
+
 }  // extern "C"
