@@ -13,7 +13,7 @@ import subprocess
 
 import numpy as np
 
-from .ctypes_defs import (Batch, COV_SIZE, LinsBatchDesc, LinsParams, LinsReport, LinsScanResult, POINT_DTYPE,
+from .ctypes_defs import (Batch, COV_SIZE, LinsBatchDesc, LinsMapReport, LinsParams, LinsReport, LinsScanResult, POINT_DTYPE,
                           SCAN_RESULT_DTYPE, STATE_DIM, as_points, ptr)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
@@ -27,7 +27,7 @@ EXPORTS = [
     "lins_gpu_set_map", "lins_gpu_ieskf", "lins_gpu_associate", "lins_gpu_estimate_transform", "lins_gpu_update_map",
     "lins_gpu_batch_upload", "lins_gpu_batch_run", "lins_gpu_batch_download", "lins_gpu_ieskf_batch",
     "lins_gpu_batch_results_device", "lins_gpu_batch_jacobian_pass", "lins_gpu_launch_count", "lins_gpu_sync",
-    "lins_gpu_debug_phase_cycles",
+    "lins_gpu_debug_phase_cycles", "lins_gpu_map_set", "lins_gpu_scan2map", "lins_gpu_map_associate",
 ]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
@@ -78,6 +78,9 @@ def lib():
         L.lins_gpu_launch_count.restype = C.c_int64
         L.lins_gpu_sync.argtypes = [vp]
         L.lins_gpu_debug_phase_cycles.argtypes = [vp, C.c_int, vp]
+        L.lins_gpu_map_set.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+        L.lins_gpu_scan2map.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.POINTER(LinsMapReport)]
+        L.lins_gpu_map_associate.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp] + [vp] * 6
         _LIB = L
     return _LIB
 
@@ -173,6 +176,29 @@ class LinsGpu:
         rep = C.c_int(0)
         self._ck(self.L.lins_gpu_update_map(self.h, ptr(s), len(s), ptr(c), len(c), ptr(st), C.byref(rep)))
         return s, c, bool(rep.value)
+
+    # ---- row F2: scan-to-map refinement of the mapping node ---------------------------------------------------------
+    def map_set(self, corner_from_map, surf_from_map):
+        c, s = as_points(corner_from_map), as_points(surf_from_map)
+        self._ck(self.L.lins_gpu_map_set(self.h, ptr(c), len(c), ptr(s), len(s)))
+
+    def scan2map(self, corner_last, surf_last, transform):
+        """≙ the iteration loop of scan2MapOptimization; returns (transformTobeMapped, LinsMapReport)."""
+        c, s = as_points(corner_last), as_points(surf_last)
+        t = np.array(transform, np.float32).copy()
+        rep = LinsMapReport()
+        self._ck(self.L.lins_gpu_scan2map(self.h, ptr(c), len(c), ptr(s), len(s), ptr(t), C.byref(rep)))
+        return t, rep
+
+    def map_associate(self, corner_last, surf_last, transform):
+        c, s = as_points(corner_last), as_points(surf_last)
+        t = np.ascontiguousarray(transform, np.float32)
+        out = dict(corner_knn=np.zeros((len(c), 5), np.int32), surf_knn=np.zeros((len(s), 5), np.int32),
+                   corner_coeff=np.zeros((len(c), 4), np.float32), surf_coeff=np.zeros((len(s), 4), np.float32),
+                   corner_mask=np.zeros(len(c), np.uint8), surf_mask=np.zeros(len(s), np.uint8))
+        self._ck(self.L.lins_gpu_map_associate(self.h, ptr(c), len(c), ptr(s), len(s), ptr(t), ptr(out["corner_knn"]), ptr(out["surf_knn"]),
+                                               ptr(out["corner_coeff"]), ptr(out["surf_coeff"]), ptr(out["corner_mask"]), ptr(out["surf_mask"])))
+        return out
 
     # ---- batched mode ------------------------------------------------------------------------------------------
     def batch_upload(self, batch: Batch):

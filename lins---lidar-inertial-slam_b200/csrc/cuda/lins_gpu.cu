@@ -22,7 +22,9 @@
 
 #include "../host/math_utils.hpp"
 #include "../host/small_linalg.hpp"
+#include "../host/lins_map_host.hpp"
 #include "lins_assoc.cuh"
+#include "lins_map.cuh"
 
 using namespace lins_dev;
 
@@ -498,6 +500,22 @@ struct lins_ctx {
   DevBuf<float4> tmp_pts;
   DevBuf<double> tmp_lin;
   PinBuf<float4> h_tmp;
+  // row F2 (scan-to-map refinement): the map clouds, the current feature clouds, search / reduction scratch
+  struct MapState {
+    DevBuf<float4> map_c, map_s, q_c, q_s;
+    int n_map_c = -1, n_map_s = -1;
+    DevBuf<float> part_d;
+    DevBuf<int> part_i;
+    DevBuf<double> partial;
+    PinBuf<double> h_partial;
+    DevBuf<int32_t> knn_c, knn_s;
+    DevBuf<float> coeff_c, coeff_s;
+    DevBuf<uint8_t> mask_c, mask_s;
+    void release() {
+      map_c.release(); map_s.release(); q_c.release(); q_s.release(); part_d.release(); part_i.release(); partial.release();
+      h_partial.release(); knn_c.release(); knn_s.release(); coeff_c.release(); coeff_s.release(); mask_c.release(); mask_s.release();
+    }
+  } mp;
 };
 
 namespace {
@@ -719,7 +737,7 @@ void lins_gpu_destroy(lins_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ctx->batch.release(); ctx->single.release();
   ctx->map_s.release(); ctx->map_c.release(); ctx->tree_s.release(); ctx->tree_c.release(); ctx->map_off.release();
-  ctx->tmp_pts.release(); ctx->tmp_lin.release(); ctx->h_tmp.release();
+  ctx->tmp_pts.release(); ctx->tmp_lin.release(); ctx->h_tmp.release(); ctx->mp.release();
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -945,6 +963,157 @@ int lins_gpu_debug_phase_cycles(lins_ctx* ctx, int enable, long long* out) {
     CK(cudaMemcpy(out, ctx->batch.timers.p, sizeof(long long) * 64, cudaMemcpyDeviceToHost));
   }
   ctx->timers_on = enable != 0;
+  return LINS_OK;
+}
+
+
+// ---- row F2: the mapping node's scan-to-map refinement (lidar_mapping_node.cpp:1635-1652) --------------------------------
+namespace {
+
+int map_upload(lins_ctx* ctx, DevBuf<float4>& dst, const lins_point* src, int n) {
+  CK(dst.reserve((size_t)n + 1));
+  if (n > 0) {
+    CK(ctx->h_tmp.reserve((size_t)n + 1));
+    CK(cudaStreamSynchronize(ctx->stream));  // the staging buffer may still feed an earlier copy
+    pack_into(ctx->h_tmp.p, src, n);
+    CK(cudaMemcpyAsync(dst.p, ctx->h_tmp.p, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return LINS_OK;
+}
+
+// one cornerOptimization + surfOptimization pass at T; AtA (6x6) / AtB (6) in f32 and the number of selected points
+int map_pass(lins_ctx* ctx, int nc, int ns, const float* T, bool dense, float* AtA, float* AtB, int* n_sel) {
+  using namespace lins_map;
+  lins_ctx::MapState& m = ctx->mp;
+  PassConsts pc;
+  pc.cRoll = std::cos(T[0]); pc.sRoll = std::sin(T[0]); pc.cPitch = std::cos(T[1]); pc.sPitch = std::sin(T[1]);
+  pc.cYaw = std::cos(T[2]); pc.sYaw = std::sin(T[2]); pc.tX = T[3]; pc.tY = T[4]; pc.tZ = T[5];
+  pc.srx = std::sin(T[0]); pc.crx = std::cos(T[0]); pc.sry = std::sin(T[1]); pc.cry = std::cos(T[1]);
+  pc.srz = std::sin(T[2]); pc.crz = std::cos(T[2]);
+  const int qb[2] = {(nc + kKnnThreads - 1) / kKnnThreads, (ns + kKnnThreads - 1) / kKnnThreads};
+  const int nq[2] = {nc, ns}, nm[2] = {std::max(m.n_map_c, 0), std::max(m.n_map_s, 0)};
+  const float4* q[2] = {m.q_c.p, m.q_s.p};
+  const float4* mp[2] = {m.map_c.p, m.map_s.p};
+  int slices[2], slice_len[2];
+  size_t part = 0;
+  for (int k = 0; k < 2; ++k) {
+    // enough (query block, map slice) pairs to cover the SMs twice; a slice is at least one tile
+    int S = qb[k] > 0 ? (2 * ctx->sm_count + qb[k] - 1) / qb[k] : 1;
+    S = std::max(1, std::min(S, std::min(64, (nm[k] + kTile - 1) / kTile)));
+    slices[k] = S;
+    slice_len[k] = std::max(1, (nm[k] + S - 1) / S);
+    part = std::max(part, (size_t)nq[k] * S * 5);
+  }
+  CK(m.part_d.reserve(part + 1)); CK(m.part_i.reserve(part + 1));
+  const int nblocks = qb[0] + qb[1];
+  CK(m.partial.reserve((size_t)(nblocks + 1) * (kRowAcc + 1))); CK(m.h_partial.reserve((size_t)(nblocks + 1) * (kRowAcc + 1)));
+  if (dense) {
+    CK(m.knn_c.reserve(5 * (size_t)nc + 1)); CK(m.knn_s.reserve(5 * (size_t)ns + 1)); CK(m.coeff_c.reserve(4 * (size_t)nc + 1));
+    CK(m.coeff_s.reserve(4 * (size_t)ns + 1)); CK(m.mask_c.reserve((size_t)nc + 1)); CK(m.mask_s.reserve((size_t)ns + 1));
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (nq[k] == 0) continue;
+    lins_map_knn_kernel<<<dim3(qb[k], slices[k]), kKnnThreads, 0, ctx->stream>>>(q[k], nq[k], mp[k], nm[k], slice_len[k], pc, m.part_d.p, m.part_i.p);
+    double* partial = m.partial.p + (size_t)(k == 0 ? 0 : qb[0]) * (kRowAcc + 1);
+    if (k == 0)
+      lins_map_fit_kernel<true><<<qb[k], kFitThreads, 0, ctx->stream>>>(q[k], nq[k], mp[k], slices[k], m.part_d.p, m.part_i.p, pc, dense ? m.knn_c.p : nullptr,
+                                                                       dense ? m.coeff_c.p : nullptr, dense ? m.mask_c.p : nullptr, partial);
+    else
+      lins_map_fit_kernel<false><<<qb[k], kFitThreads, 0, ctx->stream>>>(q[k], nq[k], mp[k], slices[k], m.part_d.p, m.part_i.p, pc, dense ? m.knn_s.p : nullptr,
+                                                                        dense ? m.coeff_s.p : nullptr, dense ? m.mask_s.p : nullptr, partial);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
+  double acc[kRowAcc + 1] = {0};
+  if (nblocks > 0) {
+    CK(cudaMemcpyAsync(m.h_partial.p, m.partial.p, sizeof(double) * (size_t)nblocks * (kRowAcc + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < nblocks; ++b)  // fixed order: corner blocks, then surf blocks (laserCloudOri's order)
+      for (int k = 0; k <= kRowAcc; ++k) acc[k] += m.h_partial.p[(size_t)b * (kRowAcc + 1) + k];
+  }
+  int k = 0;
+  for (int a = 0; a < 6; ++a)
+    for (int c = a; c < 6; ++c) { AtA[a * 6 + c] = (float)acc[k]; AtA[c * 6 + a] = (float)acc[k]; ++k; }
+  for (int a = 0; a < 6; ++a) AtB[a] = (float)acc[21 + a];
+  *n_sel = (int)acc[kRowAcc];
+  return LINS_OK;
+}
+
+int map_stage_queries(lins_ctx* ctx, const lins_point* corner, int nc, const lins_point* surf, int ns) {
+  if (nc < 0 || ns < 0 || (nc > 0 && !corner) || (ns > 0 && !surf)) return fail(ctx, LINS_E_INVALID, "bad feature clouds");
+  if (ctx->mp.n_map_c < 0) return fail(ctx, LINS_E_NOMAP, "lins_gpu_map_set has not been called");
+  int rc = map_upload(ctx, ctx->mp.q_c, corner, nc);
+  if (rc != LINS_OK) return rc;
+  return map_upload(ctx, ctx->mp.q_s, surf, ns);
+}
+
+}  // namespace
+
+int lins_gpu_map_set(lins_ctx* ctx, const lins_point* corner, int nc, const lins_point* surf, int ns) {
+  if (!ctx) return LINS_E_INVALID;
+  if (nc < 0 || ns < 0 || (nc > 0 && !corner) || (ns > 0 && !surf)) return fail(ctx, LINS_E_INVALID, "bad map clouds");
+  CK(cudaSetDevice(ctx->device));
+  int rc = map_upload(ctx, ctx->mp.map_c, corner, nc);
+  if (rc != LINS_OK) return rc;
+  rc = map_upload(ctx, ctx->mp.map_s, surf, ns);
+  if (rc != LINS_OK) return rc;
+  ctx->mp.n_map_c = nc; ctx->mp.n_map_s = ns;
+  return LINS_OK;
+}
+
+int lins_gpu_scan2map(lins_ctx* ctx, const lins_point* corner, int nc, const lins_point* surf, int ns, float* T, lins_map_report* rep) {
+  if (!ctx) return LINS_E_INVALID;
+  if (!T) return fail(ctx, LINS_E_INVALID, "null transform");
+  CK(cudaSetDevice(ctx->device));
+  lins_map_report r;
+  std::memset(&r, 0, sizeof(r));
+  if (ctx->mp.n_map_c < 0) return fail(ctx, LINS_E_NOMAP, "lins_gpu_map_set has not been called");
+  if (!(ctx->mp.n_map_c > 10 && ctx->mp.n_map_s > 100)) {  // :1636
+    r.skipped = 1;
+    if (rep) *rep = r;
+    return LINS_OK;
+  }
+  int rc = map_stage_queries(ctx, corner, nc, surf, ns);
+  if (rc != LINS_OK) return rc;
+  lins::mapping::LmState st;
+  for (int iter = 0; iter < LINS_MAP_MAX_ITER; ++iter) {
+    float AtA[36], AtB[6];
+    int n_sel = 0;
+    rc = map_pass(ctx, nc, ns, T, false, AtA, AtB, &n_sel);
+    if (rc != LINS_OK) return rc;
+    r.iters = iter + 1;
+    r.n_sel[iter] = n_sel;
+    if (n_sel < 50) continue;  // LMOptimization returns false before touching the transform (:1535-1537)
+    float dR = 0, dT = 0;
+    const bool conv = lins::mapping::lm_step(AtA, AtB, iter, T, st, dR, dT);
+    r.delta_r[iter] = dR; r.delta_t[iter] = dT;
+    r.degenerate = st.isDegenerate ? 1 : 0;
+    if (conv) { r.converged = 1; break; }
+  }
+  if (rep) *rep = r;
+  return LINS_OK;
+}
+
+int lins_gpu_map_associate(lins_ctx* ctx, const lins_point* corner, int nc, const lins_point* surf, int ns, const float* T,
+                           int32_t* cknn, int32_t* sknn, float* ccoeff, float* scoeff, uint8_t* cmask, uint8_t* smask) {
+  if (!ctx) return LINS_E_INVALID;
+  if (!T) return fail(ctx, LINS_E_INVALID, "null transform");
+  CK(cudaSetDevice(ctx->device));
+  int rc = map_stage_queries(ctx, corner, nc, surf, ns);
+  if (rc != LINS_OK) return rc;
+  float AtA[36], AtB[6];
+  int n_sel = 0;
+  rc = map_pass(ctx, nc, ns, T, true, AtA, AtB, &n_sel);
+  if (rc != LINS_OK) return rc;
+  lins_ctx::MapState& m = ctx->mp;
+  if (cknn && nc) CK(cudaMemcpyAsync(cknn, m.knn_c.p, sizeof(int32_t) * 5 * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (sknn && ns) CK(cudaMemcpyAsync(sknn, m.knn_s.p, sizeof(int32_t) * 5 * (size_t)ns, cudaMemcpyDeviceToHost, ctx->stream));
+  if (ccoeff && nc) CK(cudaMemcpyAsync(ccoeff, m.coeff_c.p, sizeof(float) * 4 * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (scoeff && ns) CK(cudaMemcpyAsync(scoeff, m.coeff_s.p, sizeof(float) * 4 * (size_t)ns, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cmask && nc) CK(cudaMemcpyAsync(cmask, m.mask_c.p, (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (smask && ns) CK(cudaMemcpyAsync(smask, m.mask_s.p, (size_t)ns, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return LINS_OK;
 }
 

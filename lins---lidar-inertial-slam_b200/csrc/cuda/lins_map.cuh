@@ -1,0 +1,257 @@
+// lins_map.cuh — row F2 of SURVEY.md §8(f): the mapping node's scan-to-map refinement on the device.
+//   reference: lins/src/lidar_mapping_node.cpp  cornerOptimization :1351-1461, surfOptimization :1463-1524,
+//              LMOptimization :1526-1633 (rows of matA / matB), pointAssociateToMap :594-608
+// Split of one iteration:
+//   lins_map_knn_kernel   exact 5-NN of every (re-projected) feature point in the map, brute force: the map is
+//                         streamed through shared memory in tiles and cut into slices across the grid so that all
+//                         SMs work (a few thousand queries alone would fill only ~25 CTAs); every (query, slice)
+//                         pair leaves a sorted partial list.  f32 ((dx*dx)+dy*dy)+dz*dz, ascending (distance, index).
+//   lins_map_fit_kernel   merges the partial lists, then per point: line fit (covariance + cv::eigen 3x3) or plane
+//                         fit (cv::solve QR 5x3), validity tests, weight, coefficients, the row of matA / matB, and
+//                         the f64 block reduction of A^T A (21) and A^T B (6).
+//   host                  sums the block partials in a fixed order, rounds to f32 and takes the 6x6 LM step
+//                         (lins_map_host.hpp).  sin / cos of the transform are evaluated on the host in f32 (6 values
+//                         per iteration), so everything the device computes is f32 + - * / sqrt, which IEEE fixes bit
+//                         for bit: indices, coefficients and masks equal the CPU oracle exactly.
+// The small OpenCV kernels (cv::eigen = cyclic Jacobi, cv::solve(DECOMP_QR) = Householder) are restated in
+// lins_cv_small.hpp, shared by host and device.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../host/lins_cv_small.hpp"
+
+namespace lins_map {
+
+constexpr int kKnnThreads = 128;
+constexpr int kTile = 2048;      // map points per shared-memory tile (32 KB)
+constexpr int kFitThreads = 128;
+constexpr int kRowAcc = 27;      // 21 (upper triangle of A^T A) + 6 (A^T B)
+
+struct PassConsts {
+  float cRoll, sRoll, cPitch, sPitch, cYaw, sYaw, tX, tY, tZ;  // updatePointAssociateToMapSinCos :579-592
+  float srx, crx, sry, cry, srz, crz;                          // LMOptimization :1527-1532
+};
+
+__device__ __forceinline__ float3 associate_to_map(const float4 pi, const PassConsts& c) {  // :594-608
+  const float x1 = c.cYaw * pi.x - c.sYaw * pi.y;
+  const float y1 = c.sYaw * pi.x + c.cYaw * pi.y;
+  const float z1 = pi.z;
+  const float x2 = x1;
+  const float y2 = c.cRoll * y1 - c.sRoll * z1;
+  const float z2 = c.sRoll * y1 + c.cRoll * z1;
+  return make_float3(c.cPitch * x2 + c.sPitch * z2 + c.tX, y2 + c.tY, -c.sPitch * x2 + c.cPitch * z2 + c.tZ);
+}
+
+struct Top5 {
+  float d[5];
+  int i[5];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { d[k] = __int_as_float(0x7f800000); i[k] = -1; }
+  }
+  // strict <: among equal distances the earlier (lower) index stays in front
+  __device__ __forceinline__ void insert(float dist, int idx) {
+    if (!(dist < d[4])) return;
+    d[4] = dist; i[4] = idx;
+#pragma unroll
+    for (int k = 4; k > 0; --k) {
+      if (d[k] < d[k - 1]) { const float td = d[k]; d[k] = d[k - 1]; d[k - 1] = td; const int ti = i[k]; i[k] = i[k - 1]; i[k - 1] = ti; }
+    }
+  }
+};
+
+// grid (query blocks, slices).  part_d / part_i: [n_q][n_slices][5]
+__global__ void __launch_bounds__(kKnnThreads) lins_map_knn_kernel(const float4* __restrict__ q, int n_q, const float4* __restrict__ map, int n_map,
+                                                                   int slice_len, PassConsts pc, float* __restrict__ part_d,
+                                                                   int* __restrict__ part_i) {
+  __shared__ float4 tile[kTile];
+  const int qi = blockIdx.x * kKnnThreads + threadIdx.x;
+  const int slice = blockIdx.y, n_slices = gridDim.y;
+  const int m0 = slice * slice_len, m1 = min(n_map, m0 + slice_len);
+  float3 s = make_float3(0.f, 0.f, 0.f);
+  if (qi < n_q) s = associate_to_map(__ldg(&q[qi]), pc);
+  Top5 t;
+  t.init();
+  for (int base = m0; base < m1; base += kTile) {
+    const int cnt = min(kTile, m1 - base);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += kKnnThreads) tile[j] = __ldg(&map[base + j]);
+    __syncthreads();
+    if (qi < n_q) {
+#pragma unroll 4
+      for (int j = 0; j < cnt; ++j) {
+        const float4 m = tile[j];  // same address for the whole warp: a broadcast
+        const float dx = __fsub_rn(s.x, m.x), dy = __fsub_rn(s.y, m.y), dz = __fsub_rn(s.z, m.z);
+        const float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        if (dist < t.d[4]) t.insert(dist, base + j);
+      }
+    }
+  }
+  if (qi < n_q) {
+    const size_t o = ((size_t)qi * n_slices + slice) * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { part_d[o + k] = t.d[k]; part_i[o + k] = t.i[k]; }
+  }
+}
+
+struct FitOut { float c[4]; bool sel; };
+
+// the body of cornerOptimization for one point (:1360-1458)
+__device__ __forceinline__ FitOut corner_fit(const float4* __restrict__ map, const float3 sel, const int ind[5], const float dist[5]) {
+  FitOut o;
+  o.c[0] = o.c[1] = o.c[2] = o.c[3] = 0.f; o.sel = false;
+  if (!(dist[4] < 1.0)) return o;
+  float px[5], py[5], pz[5];
+  float cx = 0, cy = 0, cz = 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { const float4 m = __ldg(&map[ind[j]]); px[j] = m.x; py[j] = m.y; pz[j] = m.z; cx += m.x; cy += m.y; cz += m.z; }
+  cx /= 5; cy /= 5; cz /= 5;
+  float a11 = 0, a12 = 0, a13 = 0, a22 = 0, a23 = 0, a33 = 0;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const float ax = px[j] - cx, ay = py[j] - cy, az = pz[j] - cz;
+    a11 += ax * ax; a12 += ax * ay; a13 += ax * az; a22 += ay * ay; a23 += ay * az; a33 += az * az;
+  }
+  a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
+  float A[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33}, D[3], V[9];
+  lins_cv::jacobi_eigen<3>(A, D, V);
+  if (D[0] > 3 * D[1]) {
+    const float x0 = sel.x, y0 = sel.y, z0 = sel.z;
+    const float x1 = (float)((double)cx + 0.1 * (double)V[0]), y1 = (float)((double)cy + 0.1 * (double)V[1]), z1 = (float)((double)cz + 0.1 * (double)V[2]);
+    const float x2 = (float)((double)cx - 0.1 * (double)V[0]), y2 = (float)((double)cy - 0.1 * (double)V[1]), z2 = (float)((double)cz - 0.1 * (double)V[2]);
+    const float m11 = (x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1);
+    const float m12 = (x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1);
+    const float m13 = (y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1);
+    const float a012 = sqrtf(m11 * m11 + m12 * m12 + m13 * m13);
+    const float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+    const float la = ((y1 - y2) * m11 + (z1 - z2) * m12) / a012 / l12;
+    const float lb = -((x1 - x2) * m11 - (z1 - z2) * m13) / a012 / l12;
+    const float lc = -((x1 - x2) * m12 + (y1 - y2) * m13) / a012 / l12;
+    const float ld2 = a012 / l12;
+    const float s = (float)(1 - 0.9 * (double)fabsf(ld2));
+    o.c[0] = s * la; o.c[1] = s * lb; o.c[2] = s * lc; o.c[3] = s * ld2;
+    o.sel = (double)s > 0.1;
+  }
+  return o;
+}
+
+// the body of surfOptimization for one point (:1471-1521)
+__device__ __forceinline__ FitOut surf_fit(const float4* __restrict__ map, const float3 sel, const int ind[5], const float dist[5]) {
+  FitOut o;
+  o.c[0] = o.c[1] = o.c[2] = o.c[3] = 0.f; o.sel = false;
+  if (!(dist[4] < 1.0)) return o;
+  float A0[15], B0[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
+  float px[5], py[5], pz[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) { const float4 m = __ldg(&map[ind[j]]); px[j] = m.x; py[j] = m.y; pz[j] = m.z; A0[3 * j] = m.x; A0[3 * j + 1] = m.y; A0[3 * j + 2] = m.z; }
+  float pa = 0, pb = 0, pc = 0, pd = 1;
+  if (lins_cv::qr_solve<5, 3>(A0, B0)) { pa = B0[0]; pb = B0[1]; pc = B0[2]; }  // a failed cv::solve zeroes its output
+  const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+  pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+  bool planeValid = true;
+#pragma unroll
+  for (int j = 0; j < 5; ++j)
+    if ((double)fabsf(pa * px[j] + pb * py[j] + pc * pz[j] + pd) > 0.2) planeValid = false;
+  if (planeValid) {
+    const float pd2 = pa * sel.x + pb * sel.y + pc * sel.z + pd;
+    const float s = (float)(1 - 0.9 * (double)fabsf(pd2) / (double)sqrtf(sqrtf(sel.x * sel.x + sel.y * sel.y + sel.z * sel.z)));
+    o.c[0] = s * pa; o.c[1] = s * pb; o.c[2] = s * pc; o.c[3] = s * pd2;
+    o.sel = (double)s > 0.1;
+  }
+  return o;
+}
+
+// one row of matA / matB (:1549-1593)
+__device__ __forceinline__ void lm_row(const float4 po, const float* c, const PassConsts& k, float row[6], float& b) {
+  const float srx = k.srx, crx = k.crx, sry = k.sry, cry = k.cry, srz = k.srz, crz = k.crz;
+  row[0] = (crx * sry * srz * po.x + crx * crz * sry * po.y - srx * sry * po.z) * c[0] +
+           (-srx * srz * po.x - crz * srx * po.y - crx * po.z) * c[1] +
+           (crx * cry * srz * po.x + crx * cry * crz * po.y - cry * srx * po.z) * c[2];
+  row[1] = ((cry * srx * srz - crz * sry) * po.x + (sry * srz + cry * crz * srx) * po.y + crx * cry * po.z) * c[0] +
+           ((-cry * crz - srx * sry * srz) * po.x + (cry * srz - crz * srx * sry) * po.y - crx * sry * po.z) * c[2];
+  row[2] = ((crz * srx * sry - cry * srz) * po.x + (-cry * crz - srx * sry * srz) * po.y) * c[0] +
+           (crx * crz * po.x - crx * srz * po.y) * c[1] +
+           ((sry * srz + cry * crz * srx) * po.x + (crz * sry - cry * srx * srz) * po.y) * c[2];
+  row[3] = c[0]; row[4] = c[1]; row[5] = c[2];
+  b = -c[3];
+}
+
+// One thread per feature point.  partial: [gridDim.x][kRowAcc + 1] (the last entry = selected points of the block).
+template <bool CORNER>
+__global__ void __launch_bounds__(kFitThreads) lins_map_fit_kernel(const float4* __restrict__ q, int n_q, const float4* __restrict__ map,
+                                                                   int n_slices, const float* __restrict__ part_d,
+                                                                   const int* __restrict__ part_i, PassConsts pc, int32_t* __restrict__ knn_out,
+                                                                   float* __restrict__ coeff_out, uint8_t* __restrict__ mask_out,
+                                                                   double* __restrict__ partial) {
+  const int qi = blockIdx.x * kFitThreads + threadIdx.x;
+  double acc[kRowAcc];
+#pragma unroll
+  for (int k = 0; k < kRowAcc; ++k) acc[k] = 0.0;
+  int nsel = 0;
+  if (qi < n_q) {
+    // merge the slices' sorted lists: slices are ascending index ranges, so "strictly smaller displaces" keeps the
+    // lower index in front among equal distances
+    Top5 t;
+    t.init();
+    for (int s = 0; s < n_slices; ++s) {
+      const size_t o = ((size_t)qi * n_slices + s) * 5;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int idx = part_i[o + k];
+        if (idx >= 0) t.insert(part_d[o + k], idx);
+      }
+    }
+    const float4 po = __ldg(&q[qi]);
+    const float3 sel = associate_to_map(po, pc);
+    const FitOut f = CORNER ? corner_fit(map, sel, t.i, t.d) : surf_fit(map, sel, t.i, t.d);
+    if (knn_out) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) knn_out[5 * (size_t)qi + k] = t.i[k];
+    }
+    if (coeff_out) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) coeff_out[4 * (size_t)qi + k] = f.c[k];
+    }
+    if (mask_out) mask_out[qi] = f.sel ? 1 : 0;
+    if (f.sel) {
+      float row[6], b;
+      lm_row(po, f.c, pc, row, b);
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a)
+#pragma unroll
+        for (int c = a; c < 6; ++c) acc[k++] = (double)row[a] * (double)row[c];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) acc[21 + a] = (double)row[a] * (double)b;
+      nsel = 1;
+    }
+  }
+  // fixed-tree block reduction (deterministic)
+  __shared__ double wsum[kFitThreads / 32][kRowAcc];
+  __shared__ int wcnt[kFitThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kRowAcc; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) wsum[warp][k] = v;
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) nsel += __shfl_xor_sync(0xffffffffu, nsel, m);
+  if (lane == 0) wcnt[warp] = nsel;
+  __syncthreads();
+  if (threadIdx.x < kRowAcc) {
+    double v = 0;
+    for (int w = 0; w < kFitThreads / 32; ++w) v += wsum[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * (kRowAcc + 1) + threadIdx.x] = v;
+  }
+  if (threadIdx.x == kRowAcc) {
+    int c = 0;
+    for (int w = 0; w < kFitThreads / 32; ++w) c += wcnt[w];
+    partial[(size_t)blockIdx.x * (kRowAcc + 1) + kRowAcc] = (double)c;
+  }
+}
+
+}  // namespace lins_map

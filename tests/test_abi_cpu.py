@@ -33,6 +33,15 @@ def test_struct_layouts_match_header(defs):
     assert C.sizeof(defs.LinsParams) == 48
     assert C.sizeof(defs.LinsReport) == 16 + 64 * 4 * 2 + 64 * 8 * 2
     assert C.sizeof(defs.LinsBatchDesc) == 8 + 10 * 8
+    assert C.sizeof(defs.LinsMapReport) == 4 * 4 + 3 * 10 * 4  # row F2
+    # the C side agrees (compile the header with gcc and print the sizes)
+    import subprocess, tempfile
+    src = '#include <stdio.h>\n#include "lins_gpu.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(lins_scan_result), sizeof(lins_params), sizeof(lins_report), sizeof(lins_batch_desc), sizeof(lins_map_report));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "s.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "s"), os.path.join(d, "s.c")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "s")]).split()]
+    assert sizes == [C.sizeof(t) for t in (defs.LinsScanResult, defs.LinsParams, defs.LinsReport, defs.LinsBatchDesc, defs.LinsMapReport)]
 
 
 @pytest.mark.skipif(have_gpu(), reason="checks the no-GPU failure mode")
