@@ -339,6 +339,26 @@ def main():
                   "algorithmic_bytes_per_launch": jbytes, "working_set_mb": (16 * sum(int(jb.offsets[k][-1]) for k in jb.FIELDS)) / 1e6}
     jctx.close()
 
+    # ---- row F2: the mapping node's scan-to-map refinement, one 50-key-frame unit ---------------------
+    mu = synth.generate_map_unit("config3", seed=40, n_keyframes=50, sigma_t=0.1, sigma_r=0.01)
+    mctx = capi.LinsGpu(prm, device=local, stream=stream.cuda_stream)
+    mctx.map_set(mu.corner_map, mu.surf_map)
+    for _ in range(2):
+        mctx.scan2map(mu.corner_last, mu.surf_last, mu.guess)
+    torch.cuda.synchronize()
+    mreps = 10
+    t0 = time.perf_counter()
+    for _ in range(mreps):
+        mT, mrep = mctx.scan2map(mu.corner_last, mu.surf_last, mu.guess)  # synchronous: H2D of the features, <= 10 x (5-NN, fits, reduce, D2H, LM)
+    mapping_ms = (time.perf_counter() - t0) * 1e3 / mreps
+    nq_map = len(mu.corner_last) + len(mu.surf_last)
+    dist_evals = (len(mu.corner_last) * len(mu.corner_map) + len(mu.surf_last) * len(mu.surf_map)) * mrep.iters
+    mapping = {"what": "lins_gpu_scan2map (lidar_mapping_node.cpp:1635-1652): exact brute-force 5-NN + line / plane fits + LM, host buffers in / out",
+               "map_points": int(len(mu.corner_map) + len(mu.surf_map)), "feature_points": int(nq_map), "lm_iterations": int(mrep.iters),
+               "converged": int(mrep.converged), "ms_per_call": mapping_ms, "distance_evaluations_per_s": dist_evals / (mapping_ms * 1e-3),
+               "translation_error_m": {"before": float(np.abs(mu.guess[3:] - mu.truth[3:]).max()), "after": float(np.abs(mT[3:] - mu.truth[3:]).max())}}
+    mctx.close()
+
     # ---- CPU baseline (rank 0, N = 1 only): oracle on the host cores, bounded sample ---------------------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -351,6 +371,12 @@ def main():
         cpu = {"value": itsA / secA, "unit": "iterations/s", "cores": cores, "kind": "port",
                "sample": f"first {sample} scans of batch 0; reference-faithful MxM gain (form A), kd-tree 1-NN, {cores} scan-parallel threads",
                "form_b_18x18_1thread_iters_per_s": itsB1 / secB1, "form_b_18x18_allcores_iters_per_s": itsBn / secBn}
+        mo = ob.MapOracle()
+        mo.set_map(mu.corner_map, mu.surf_map)
+        t0 = time.perf_counter()
+        moT, morep = mo.scan2map(mu.corner_last, mu.surf_last, mu.guess)
+        mapping["cpu_port_ms_per_call"] = (time.perf_counter() - t0) * 1e3  # 1 thread, brute-force 5-NN like the device
+        mapping["max_abs_transform_diff_vs_cpu_port"] = float(np.abs(moT - mT).max())
 
     out = {
         "metric": "ESKF iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -362,7 +388,7 @@ def main():
         "clocks": clk,
         "e2e": {"value": e2e_iters / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "host_threads": NE},
         "gpu_launches": int(total_launches),
-        "roofline": roofline, "roofline_jacobian": roofline_j,
+        "roofline": roofline, "roofline_jacobian": roofline_j, "mapping_refinement": mapping,
     }
     if cpu:
         out["cpu_baseline"] = cpu
