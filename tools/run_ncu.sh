@@ -1,5 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-md5sum lins---lidar-inertial-slam_b200/liblins_gpu.so | cut -c1-8 > gpurun_out/build_id.txt
-ncu --set full --clock-control none --import-source on -k regex:lins_ieskf -s 4 -c 1 -o gpurun_out/prof_r01_b python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/prof_b.log 2>&1
-cat gpurun_out/build_id.txt; ls -la gpurun_out | tail -n 4
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_r01_map.csv python tools/map_bench.py > gpurun_out/map_under_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:lins_map_knn -s 3 -c 1 -o gpurun_out/prof_r01_map_knn python tools/map_bench.py > gpurun_out/prof_map1.log 2>&1
+ncu --set full --clock-control none -k regex:lins_map_fit -s 3 -c 1 -o gpurun_out/prof_r01_map_fit python tools/map_bench.py > gpurun_out/prof_map2.log 2>&1
+python tools/map_bench.py
+ls -la gpurun_out | tail -n 6
