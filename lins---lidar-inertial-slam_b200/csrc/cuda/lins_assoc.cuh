@@ -32,6 +32,7 @@ struct PassBuffers {
   float4* qref;              // fast path: pointSel at the last closest-point search + the slack (m) of its answer
   float4* qref2;             // fast path: pointSel at the last walk search + the slack of Ind2 / Ind3
   int* qccr;                 // fast path: (ring << 24 | original index) of the closest point, -1 = none
+  float4* qext;              // fast path: (bound / slack of the Ind3 search, runner-up slots of closest / Ind2 / Ind3 as int bits)
   int* wl;                   // fast path: work list of the queries that need a closest-point search / ring walks this pass
   const float4* azS;         // sorted copies (shared or global)
   const float4* azC;
@@ -108,11 +109,23 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         const float4 s = pb.sel[i];
         const bool surf = i < nsT;
         float4 qa = make_float4(0.f, 0.f, -1.f, 0.f);
-        if (seeded) {  // certificates: displaced by less than half the slack since the search => same answer
-          const float4 r1 = pb.qref[i], r2 = pb.qref2[i];
-          const bool ok1 = r1.w > 0.f && 2.0f * sqrtf(sqdist_f32(s.x, s.y, s.z, r1.x, r1.y, r1.z)) + 2.0e-4f < r1.w;
-          const bool ok2 = r2.w > 0.f && 2.0f * sqrtf(sqdist_f32(s.x, s.y, s.z, r2.x, r2.y, r2.z)) + 2.0e-4f < r2.w;
-          if (ok1 && (ok2 || pb.qccr[i] < 0)) { pb.qw[i] = make_int4(-2, 0, 0, 0); continue; }
+        if (seeded) {  // certificates (lins_assoc_az.cuh: cert_accepted / cert_rejected): the stored answers still hold
+          const float4 r1 = pb.qref[i], r2 = pb.qref2[i], ex = pb.qext[i];
+          const AzIndex& ixq = surf ? ixS : ixC;
+          const unsigned nearbits = __float_as_uint(nearf);
+          const float moved1 = sqrtf(sqdist_f32(s.x, s.y, s.z, r1.x, r1.y, r1.z));
+          const int w1s = pb.pos[3 * i];
+          const bool ok1 = w1s >= 0 ? cert_accepted<false>(ixq, s, w1s, __float_as_int(ex.y), r1.w, moved1, nearbits, 0) : cert_rejected(r1.w, moved1);
+          bool ok2 = false;
+          const int ccr0 = pb.qccr[i];
+          if (ok1 && ccr0 >= 0) {  // (the walks' candidate sets are defined by the closest point: only meaningful while it stands)
+            const int c0 = ccr0 & 0x00ffffff;
+            const float moved2 = sqrtf(sqdist_f32(s.x, s.y, s.z, r2.x, r2.y, r2.z));
+            const int w2s = pb.pos[3 * i + 1], w3s = pb.pos[3 * i + 2];
+            ok2 = w2s >= 0 ? cert_accepted<true>(ixq, s, w2s, __float_as_int(ex.z), r2.w, moved2, nearbits, c0) : cert_rejected(r2.w, moved2);
+            if (ok2 && surf) ok2 = w3s >= 0 ? cert_accepted<true>(ixq, s, w3s, __float_as_int(ex.w), ex.x, moved2, nearbits, c0) : cert_rejected(ex.x, moved2);
+          }
+          if (ok1 && (ok2 || ccr0 < 0)) { pb.qw[i] = make_int4(-2, 0, 0, 0); continue; }
           if (ok1) { az_polar(s, qa); pb.qa[i] = qa; pb.qw[i] = make_int4(-3, 0, 0, 0); continue; }
         }
         const int w1 = az_prepare_nn(surf ? ixS : ixC, s, nearf, seeded ? pb.pos[3 * i] : -1, qa);
@@ -142,8 +155,9 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         int w1 = pb.qw[i].x;
         const long long t_s0 = (diag && lane == 0) ? clock64() : 0;
         unsigned long long k1 = kKeyMax;
-        unsigned second = 0xffffffffu;
         int p1 = -1;
+        Top3 top;
+        top.init();
         const bool surf = i < nsT;
         const AzIndex& ix = surf ? ixS : ixC;
         const float4 s = pb.sel[i];
@@ -151,18 +165,22 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         if (w1 >= 0) {
           const int wp = first_pass_of_scan ? az_probe_window<kProbeNN>(ix, qa, w1) : -1;
           if (wp >= 0) {  // wide window (no usable previous answer): probe first, then search inside the implied window
-            az_scan_nn(ix, s, wp, p1, second);
-            if (p1 >= 0) {
-              w1 = az_nn_window(ix, az_seed_bound(ix, s, p1, nearf), qa);
+            const Top3 pr = az_scan_nn(ix, s, wp);
+            if (pr.p1 >= 0) {
+              w1 = az_nn_window(ix, az_seed_bound(ix, s, pr.p1, nearf), qa);
               if (lane == 0) pb.qa[i] = qa;
             }
           }
-          k1 = az_scan_nn(ix, s, w1, p1, second, tm);
+          top = az_scan_nn(ix, s, w1, tm);
+          k1 = top.k1; p1 = top.p1;
         }
         if (lane == 0) {
           const float d1 = __uint_as_float((unsigned)(k1 >> 32));
           const bool acc1 = k1 != kKeyMax && p1 >= 0 && (double)d1 < kp.nearest_sq;
-          pb.qref[i] = make_float4(s.x, s.y, s.z, w1 >= 0 ? search_slack((unsigned)(k1 >> 32), second, qa.w, gate, acc1) : -1.f);
+          // accepted: what everything but the two front-runners exceeded; else the slack of "nothing within the gate"
+          const float bound1 = w1 < 0 ? -1.f : acc1 ? cert_bound(top.d3, qa.w) : search_slack((unsigned)(k1 >> 32), (unsigned)(top.k2 >> 32), qa.w, gate, false);
+          pb.qref[i] = make_float4(s.x, s.y, s.z, bound1);
+          pb.qext[i].y = __int_as_float(acc1 ? top.p2 : -1);
           pb.pos[3 * i] = acc1 ? p1 : -1;
           pb.qccr[i] = acc1 ? ((slot_ring(ix.pts[p1].w) << 24) | (int)(unsigned)(k1 & 0xffffffffu)) : -1;
           if (diag && !first_pass_of_scan) {
@@ -227,8 +245,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         const bool surf = i < nsT;
         const int gq = q0 + i;
         float2 B = reinterpret_cast<const float2*>(pb.key)[i];
-        int i2, i3, p2, p3, w2 = w.y, w3 = w.z;
-        float slack;
+        int w2 = w.y, w3 = w.z;
         const float4 s = pb.sel[i];
         {  // wide windows (no usable previous answer): probe a small window first and re-window from what it finds
           const float4 qa = pb.qa[i];
@@ -241,20 +258,23 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
             int pw2, pw3;
             if (surf) {
               az_prepare_walk<true>(ixS, s, qa, c, cr, -1, -1, fwdS, kProbeSq, pw2, pw3, b2, b3);
-              az_scan_walk<true>(ixS, s, w.w, pw2, pw3, fwdS, nearf, b2, b3, i2, i3, p2, p3, slack);
-              az_prepare_walk<true>(ixS, s, qa, c, cr, sd2, sd3, fwdS, nearf, w2, w3, B.x, B.y, p2, p3);
+              const WalkOut pr = az_scan_walk<true>(ixS, s, w.w, pw2, pw3, fwdS, nearf, b2, b3);
+              az_prepare_walk<true>(ixS, s, qa, c, cr, sd2, sd3, fwdS, nearf, w2, w3, B.x, B.y, pr.pos2, pr.pos3);
             } else {
               az_prepare_walk<false>(ixC, s, qa, c, cr, -1, -1, fwdC, kProbeSq, pw2, pw3, b2, b3);
-              az_scan_walk<false>(ixC, s, w.w, pw2, pw3, fwdC, nearf, b2, b3, i2, i3, p2, p3, slack);
-              az_prepare_walk<false>(ixC, s, qa, c, cr, sd2, sd3, fwdC, nearf, w2, w3, B.x, B.y, p2, p3);
+              const WalkOut pr = az_scan_walk<false>(ixC, s, w.w, pw2, pw3, fwdC, nearf, b2, b3);
+              az_prepare_walk<false>(ixC, s, qa, c, cr, sd2, sd3, fwdC, nearf, w2, w3, B.x, B.y, pr.pos2, pr.pos3);
             }
           }
         }
-        if (surf) az_scan_walk<true>(ixS, s, w.w, w2, w3, fwdS, nearf, B.x, B.y, i2, i3, p2, p3, slack);
-        else az_scan_walk<false>(ixC, s, w.w, w2, w3, fwdC, nearf, B.x, B.y, i2, i3, p2, p3, slack);
+        const WalkOut wo = surf ? az_scan_walk<true>(ixS, s, w.w, w2, w3, fwdS, nearf, B.x, B.y) : az_scan_walk<false>(ixC, s, w.w, w2, w3, fwdC, nearf, B.x, B.y);
+        const int i2 = wo.i2, i3 = wo.i3;
         if (lane == 0) {
-          pb.pos[3 * i + 1] = p2; pb.pos[3 * i + 2] = p3;
-          pb.qref2[i] = make_float4(s.x, s.y, s.z, slack);
+          pb.pos[3 * i + 1] = wo.pos2; pb.pos[3 * i + 2] = wo.pos3;
+          pb.qref2[i] = make_float4(s.x, s.y, s.z, wo.bound2);
+          float4 ex = pb.qext[i];  // (.y = the closest point's runner-up, written by P2 or kept from an earlier pass)
+          ex.x = wo.bound3; ex.z = __int_as_float(wo.run2); ex.w = __int_as_float(wo.run3);
+          pb.qext[i] = ex;
           if (diag && !first_pass_of_scan) {
             const unsigned long long dt = (unsigned long long)(clock64() - t_s0);
             atomicAdd((unsigned long long*)&bv.timers[30], dt);

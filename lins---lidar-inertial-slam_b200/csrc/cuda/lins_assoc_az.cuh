@@ -195,6 +195,53 @@ __device__ __forceinline__ unsigned keep_min(unsigned long long& a, int& pa, uns
   pa = lt ? pb : pa;
   return loser;
 }
+// The two smallest keys seen so far with their slots, and the distance bits of the third.  Certificates built on the
+// third distance survive a near-tie between the two front-runners (the common reason an answer could not be certified:
+// a query almost equidistant from two neighbouring points of a ring): those two are simply re-evaluated exactly.
+struct Top3 {
+  unsigned long long k1, k2;
+  int p1, p2;
+  unsigned d3;
+  __device__ __forceinline__ void init() { k1 = kKeyMax; k2 = kKeyMax; p1 = -1; p2 = -1; d3 = 0xffffffffu; }
+  __device__ __forceinline__ void insert(unsigned long long k, int p) {  // branch-free; kKeyMax changes nothing
+    const bool lt1 = k < k1, lt2 = k < k2;
+    d3 = lt2 ? (unsigned)(k2 >> 32) : min(d3, (unsigned)(k >> 32));
+    k2 = lt1 ? k1 : (lt2 ? k : k2);
+    p2 = lt1 ? p1 : (lt2 ? p : p2);
+    k1 = lt1 ? k : k1;
+    p1 = lt1 ? p : p1;
+  }
+};
+__device__ __forceinline__ int warp_argmin_lane(unsigned long long k, unsigned long long& kmin) {
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)(k & 0xffffffffu);
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  kmin = ((unsigned long long)mhi << 32) | mlo;
+  return __ffs(__ballot_sync(0xffffffffu, hi == mhi && lo == mlo)) - 1;
+}
+// warp-wide top 3 of the lanes' Top3 (every lane receives the result)
+__device__ __forceinline__ void warp_top3(Top3& t) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long K1, K2;
+  const int a = warp_argmin_lane(t.k1, K1);
+  const int P1 = __shfl_sync(0xffffffffu, t.p1, a);
+  const unsigned long long cand = lane == a ? t.k2 : t.k1;
+  const int candp = lane == a ? t.p2 : t.p1;
+  const int b = warp_argmin_lane(cand, K2);
+  const int P2 = __shfl_sync(0xffffffffu, candp, b);
+  // the best entry each lane has left after the two front-runners were taken
+  unsigned rest;
+  if (lane == a && lane == b) rest = t.d3;
+  else if (lane == a || lane == b) rest = (unsigned)(t.k2 >> 32);
+  else rest = (unsigned)(t.k1 >> 32);
+  t.d3 = __reduce_min_sync(0xffffffffu, rest);
+  t.k1 = K1; t.p1 = K1 == kKeyMax ? -1 : P1;
+  t.k2 = K2; t.p2 = K2 == kKeyMax ? -1 : P2;
+}
+// distance (m) that every candidate other than the two front-runners exceeded at the search position
+__device__ __forceinline__ float cert_bound(unsigned third_bits, float Bout) {
+  return third_bits >= 0x7f800000u ? Bout : fminf(sqrtf(__uint_as_float(third_bits)), Bout);
+}
 // One slot of the sorted copy.  When the copy is in shared memory the load is an explicit ld.shared: the generic
 // load the compiler would otherwise emit has a longer latency and was scheduled one candidate at a time (all four
 // loads of a trip through the same registers), which left a lone warp waiting ~100 cycles per candidate.
@@ -208,8 +255,7 @@ __device__ __forceinline__ float4 ld_slot(const AzIndex& ix, int p) {
   return ix.pts[p];
 }
 template <int LPR, bool SMEM>
-__device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4 s, int p, int pe, unsigned long long& best,
-                                                 unsigned& second, int& bpos) {
+__device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4 s, int p, int pe, Top3& top) {
   for (; p < pe; p += 4 * LPR) {
     unsigned long long k[4];
     int q[4];
@@ -225,35 +271,18 @@ __device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4
       k[u] = valid ? (((unsigned long long)d << 32) | (unsigned)slot_index(t.w)) : kKeyMax;  // (kKeyMax never wins and never lowers a runner-up)
       q[u] = pu;
     }
-    const unsigned l01 = keep_min(k[0], q[0], k[1], q[1]);
-    const unsigned l23 = keep_min(k[2], q[2], k[3], q[3]);
-    const unsigned l03 = keep_min(k[0], q[0], k[2], q[2]);
-    const unsigned lb = keep_min(best, bpos, k[0], q[0]);
-    second = min(min(second, lb), min(min(l01, l23), l03));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) top.insert(k[u], q[u]);
   }
 }
-// warp arg-min that also yields the distance bits of the overall runner-up
-__device__ __forceinline__ void warp_argmin2(unsigned long long& best, unsigned& second, int& payload) {
-  const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)(best & 0xffffffffu);
-  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
-  const unsigned wmask = __ballot_sync(0xffffffffu, hi == mhi && lo == mlo);
-  const int wl = __ffs(wmask) - 1;
-  const bool winner = (int)(threadIdx.x & 31) == wl;
-  second = __reduce_min_sync(0xffffffffu, winner ? second : hi);  // every other lane's best is a runner-up candidate
-  payload = __shfl_sync(0xffffffffu, payload, wl);
-  best = ((unsigned long long)mhi << 32) | mlo;
-}
 template <int LPR, bool SMEM>
-__device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, const float4 s, int win, int& pos, unsigned& second_out,
-                                                           long long* tm = nullptr) {
+__device__ __forceinline__ Top3 az_scan_nn_t(const AzIndex& ix, const float4 s, int win, long long* tm = nullptr) {
   const int lane = threadIdx.x & 31;
   const int blo = win >> 16, nbins = win & 0xffff;
   constexpr int RPP = 32 / LPR;
   const int sub = lane % LPR;
-  unsigned long long best = kKeyMax;
-  unsigned second = 0xffffffffu;
-  int bpos = -1;
+  Top3 top;
+  top.init();
   const int e0 = min(blo + nbins, ix.nb), e1 = blo + nbins - ix.nb;
   int dbg_cand = 0;
   for (int rbase = 0; rbase < ix.nrings; rbase += RPP) {
@@ -261,28 +290,26 @@ __device__ __forceinline__ unsigned long long az_scan_nn_t(const AzIndex& ix, co
     if (r < ix.nrings) {
       const int base = r * ix.nb;
       if (tm) { dbg_cand += max(0, (ix.bstart[base + e0] - ix.bstart[base + blo] - sub + LPR - 1) / LPR); if (e1 > 0) dbg_cand += max(0, (ix.bstart[base + e1] - ix.bstart[base] - sub + LPR - 1) / LPR); }
-      az_scan_nn_slice<LPR, SMEM>(ix, s, ix.bstart[base + blo] + sub, ix.bstart[base + e0], best, second, bpos);
-      if (e1 > 0) az_scan_nn_slice<LPR, SMEM>(ix, s, ix.bstart[base] + sub, ix.bstart[base + e1], best, second, bpos);
+      az_scan_nn_slice<LPR, SMEM>(ix, s, ix.bstart[base + blo] + sub, ix.bstart[base + e0], top);
+      if (e1 > 0) az_scan_nn_slice<LPR, SMEM>(ix, s, ix.bstart[base] + sub, ix.bstart[base + e1], top);
     }
   }
   if (tm) { tm[0] = clock64(); tm[2] = __reduce_max_sync(0xffffffffu, (unsigned)dbg_cand); tm[3] = __reduce_add_sync(0xffffffffu, (unsigned)dbg_cand); }
-  warp_argmin2(best, second, bpos);
-  if ((unsigned)(best >> 32) >= 0x7f800000u) { best = kKeyMax; bpos = -1; }  // only inf / NaN distances: nothing found
-  pos = bpos;
-  second_out = second;
+  warp_top3(top);
+  if ((unsigned)(top.k1 >> 32) >= 0x7f800000u) { top.k1 = kKeyMax; top.p1 = -1; }  // only inf / NaN distances: nothing found
   if (tm) tm[1] = clock64();
-  return best;
+  return top;
 }
-__device__ __forceinline__ unsigned long long az_scan_nn(const AzIndex& ix, const float4 s, int win, int& pos, unsigned& second,
-                                                         long long* tm = nullptr) {
+// -> the two nearest (key, slot) pairs and the third distance, over every ring inside the window
+__device__ __forceinline__ Top3 az_scan_nn(const AzIndex& ix, const float4 s, int win, long long* tm = nullptr) {
   if (ix.sbase) {
-    if (ix.nrings <= 8) return az_scan_nn_t<4, true>(ix, s, win, pos, second, tm);
-    if (ix.nrings <= 16) return az_scan_nn_t<2, true>(ix, s, win, pos, second, tm);
-    return az_scan_nn_t<1, true>(ix, s, win, pos, second, tm);
+    if (ix.nrings <= 8) return az_scan_nn_t<4, true>(ix, s, win, tm);
+    if (ix.nrings <= 16) return az_scan_nn_t<2, true>(ix, s, win, tm);
+    return az_scan_nn_t<1, true>(ix, s, win, tm);
   }
-  if (ix.nrings <= 8) return az_scan_nn_t<4, false>(ix, s, win, pos, second, tm);
-  if (ix.nrings <= 16) return az_scan_nn_t<2, false>(ix, s, win, pos, second, tm);
-  return az_scan_nn_t<1, false>(ix, s, win, pos, second, tm);
+  if (ix.nrings <= 8) return az_scan_nn_t<4, false>(ix, s, win, tm);
+  if (ix.nrings <= 16) return az_scan_nn_t<2, false>(ix, s, win, tm);
+  return az_scan_nn_t<1, false>(ix, s, win, tm);
 }
 
 // ---- phase P3 (one THREAD per query): bound + window the walks of a query whose closest point is (c, cr) -------
@@ -326,18 +353,21 @@ __device__ __forceinline__ void az_prepare_walk(const AzIndex& ix, const float4 
 // ---- phase P4 (one WARP per query): the ring walks inside their windows -------------------------------------------
 // SURF: Ind2 over ring cr (window w2), Ind3 over rings cr-2, cr-1, cr+1, cr+2 (window w3).  Corner: Ind2 over rings
 // cr-2, cr-1, cr+1, cr+2 (window w2).  Forward candidates (original index j > c) count only while j < fwdBound.
+struct WalkOut {  // per class: original index (-1 = none within the gate), slot, certificate bound, runner-up slot
+  int i2, i3, pos2, pos3, run2, run3;
+  float bound2, bound3;
+};
 template <bool SURF, bool SMEM>
-__device__ __forceinline__ void az_scan_walk_t(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
-                                             float B2, float B3, int& i2, int& i3, int& pos2, int& pos3, float& slack) {
+__device__ __forceinline__ WalkOut az_scan_walk_t(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
+                                                float B2, float B3) {
   const int lane = threadIdx.x & 31;
   const int c = ccr & 0x00ffffff, cr = (int)((unsigned)ccr >> 24);
   // keys are NOT gated here: the minimum over the candidates is needed even when it lies beyond the gate (to certify
   // "still nothing within the gate"); the gate is applied to the reduced winner, which is equivalent to the
   // reference's `pointSqDis < minPointSqDis` starting from NEAREST_FEATURE_SEARCH_SQ_DIST.
-  // a lane serves one ring, hence one class: it keeps a single (best, runner-up, slot) triple
-  unsigned long long kb = kKeyMax;
-  unsigned sb = 0xffffffffu;
-  int qb = -1;
+  // a lane serves one ring, hence one class: it keeps a single Top3
+  Top3 top;
+  top.init();
   const int r = cr - 2 + lane / 6, sub = lane % 6;  // 5 rings x 6 lanes
   const bool cls2 = SURF ? (r == cr) : true;
   if (lane < 30 && r >= 0 && r < ix.nrings && (SURF || r != cr)) {
@@ -360,38 +390,65 @@ __device__ __forceinline__ void az_scan_walk_t(const AzIndex& ix, const float4 s
           const bool fwd = j > c;
           const bool adm = pu < pe && j != c && (!fwd || j < fwdBound);
           const unsigned long long k = adm ? (((unsigned long long)d << 32) | (fwd ? order_fwd(j) : order_bwd(j))) : kKeyMax;
-          sb = min(sb, keep_min(kb, qb, k, pu));  // branch-free, see az_scan_nn_slice
+          top.insert(k, pu);
         }
       }
     }
   }
   const float gate = sqrtf(nearf);
   const unsigned nearbits = __float_as_uint(nearf);
-  const bool mine2 = lane < 30 && cls2;  // (lanes outside the 5 x 6 layout hold the neutral triple)
-  unsigned long long k2 = mine2 ? kb : kKeyMax, k3 = mine2 ? kKeyMax : kb;
-  unsigned s2 = mine2 ? sb : 0xffffffffu, s3 = mine2 ? 0xffffffffu : sb;
-  int q2 = mine2 ? qb : -1, q3 = mine2 ? -1 : qb;
-  warp_argmin2(k2, s2, q2);
-  const bool ok2 = (unsigned)(k2 >> 32) < nearbits && q2 >= 0;
-  i2 = ok2 ? order_decode((unsigned)(k2 & 0xffffffffu)) : -1;
-  pos2 = ok2 ? q2 : -1;
-  slack = search_slack((unsigned)(k2 >> 32), s2, B2, gate, ok2);
-  if (SURF) {
-    warp_argmin2(k3, s3, q3);
-    const bool ok3 = (unsigned)(k3 >> 32) < nearbits && q3 >= 0;
-    i3 = ok3 ? order_decode((unsigned)(k3 & 0xffffffffu)) : -1;
-    pos3 = ok3 ? q3 : -1;
-    slack = fminf(slack, search_slack((unsigned)(k3 >> 32), s3, B3, gate, ok3));
-  } else {
-    i3 = -1; pos3 = -1;
-  }
+  const bool mine2 = lane < 30 && cls2;  // (lanes outside the 5 x 6 layout hold the neutral entry)
+  Top3 neutral;
+  neutral.init();
+  WalkOut o;
+  // accepted (within the gate): bound = distance everything but the two front-runners exceeded; otherwise the slack
+  // of "still nothing within the gate" (search_slack)
+  auto finish = [&](Top3 t, float Bout, int& idx, int& pos, int& run, float& bound) {
+    warp_top3(t);
+    const bool ok = (unsigned)(t.k1 >> 32) < nearbits && t.p1 >= 0;
+    idx = ok ? order_decode((unsigned)(t.k1 & 0xffffffffu)) : -1;
+    pos = ok ? t.p1 : -1;
+    run = ok ? t.p2 : -1;
+    bound = ok ? cert_bound(t.d3, Bout) : search_slack((unsigned)(t.k1 >> 32), (unsigned)(t.k2 >> 32), Bout, gate, false);
+  };
+  finish(mine2 ? top : neutral, B2, o.i2, o.pos2, o.run2, o.bound2);
+  if (SURF) finish(mine2 ? neutral : top, B3, o.i3, o.pos3, o.run3, o.bound3);
+  else { o.i3 = -1; o.pos3 = -1; o.run3 = -1; o.bound3 = 0.f; }
+  return o;
 }
 
 template <bool SURF>
-__device__ __forceinline__ void az_scan_walk(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
-                                             float B2, float B3, int& i2, int& i3, int& pos2, int& pos3, float& slack) {
-  if (ix.sbase) az_scan_walk_t<SURF, true>(ix, s, ccr, w2, w3, fwdBound, nearf, B2, B3, i2, i3, pos2, pos3, slack);
-  else az_scan_walk_t<SURF, false>(ix, s, ccr, w2, w3, fwdBound, nearf, B2, B3, i2, i3, pos2, pos3, slack);
+__device__ __forceinline__ WalkOut az_scan_walk(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
+                                                float B2, float B3) {
+  if (ix.sbase) return az_scan_walk_t<SURF, true>(ix, s, ccr, w2, w3, fwdBound, nearf, B2, B3);
+  return az_scan_walk_t<SURF, false>(ix, s, ccr, w2, w3, fwdBound, nearf, B2, B3);
 }
+
+// ---- certificates (phase P1, one THREAD per query) ------------------------------------------------------------------
+// An accepted answer (winner slot w >= 0) is still the answer at the query's new position s if
+//   * the winner re-evaluated exactly is still inside the gate and still beats the re-evaluated runner-up (exact keys,
+//     so ties fall like in a full search), and
+//   * it is closer than everything else can have become: bound - moved, where `bound` is what every other candidate
+//     exceeded at the search position and `moved` the displacement since (distances change by at most that much);
+//     2e-4 m absorbs the f32 rounding of the distances involved.
+// WALK: keys carry the visiting order relative to the closest point c instead of the original index.
+template <bool WALK>
+__device__ __forceinline__ bool cert_accepted(const AzIndex& ix, const float4 s, int w, int r, float bound, float moved, unsigned nearbits,
+                                              int c) {
+  auto key_of = [&](int slot) -> unsigned long long {
+    const float4 t = ix.pts[slot];
+    const unsigned d = __float_as_uint(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z));
+    const int j = slot_index(t.w);
+    const unsigned lo = WALK ? (j > c ? order_fwd(j) : order_bwd(j)) : (unsigned)j;
+    return ((unsigned long long)d << 32) | lo;
+  };
+  const unsigned long long kw = key_of(w);
+  const unsigned dw = (unsigned)(kw >> 32);
+  if (!(dw < nearbits)) return false;
+  if (r >= 0 && !(kw < key_of(r))) return false;
+  return sqrtf(__uint_as_float(dw)) + moved + 2.0e-4f < bound;
+}
+// a search that found nothing within the gate: stays that way while the query moved less than half the slack
+__device__ __forceinline__ bool cert_rejected(float slack, float moved) { return slack > 0.f && 2.0f * moved + 2.0e-4f < slack; }
 
 }  // namespace lins_dev

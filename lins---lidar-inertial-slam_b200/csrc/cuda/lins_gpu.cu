@@ -32,11 +32,11 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------------------
 // dynamic shared memory layout:
-//   [qpt float4 x Q][sel float4 x Q][qa float4 x Q][qw int4 x Q][qref, qref2 float4 x Q][key u64 x Q][pos int x 3Q][qccr int x Q][wl int x Q][Smem][azS ..][azC ..]
+//   [qpt float4 x Q][sel float4 x Q][qa float4 x Q][qw int4 x Q][qref, qref2, qext float4 x Q][key u64 x Q][pos int x 3Q][qccr int x Q][wl int x Q][Smem][azS ..][azC ..]
 // cap_s / cap_c = points of the (ring, azimuth)-sorted target copies kept in shared memory (0: global scratch)
 // ---------------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t smem_front_bytes(int qtile) {
-  size_t b = (size_t)qtile * (16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4 + 4);
+  size_t b = (size_t)qtile * (16 + 16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4 + 4);
   b = (b + 15) & ~(size_t)15;
   return b + ((sizeof(Smem) + 15) & ~(size_t)15);
 }
@@ -55,11 +55,12 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
   int4* qwbuf = reinterpret_cast<int4*>(qabuf + Q);
   float4* qrefbuf = reinterpret_cast<float4*>(qwbuf + Q);
   float4* qref2buf = qrefbuf + Q;
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(qref2buf + Q);
+  float4* qextbuf = qref2buf + Q;
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(qextbuf + Q);
   int* posbuf = reinterpret_cast<int*>(key + Q);
   int* qccrbuf = posbuf + 3 * Q;
   int* wlbuf = qccrbuf + Q;
-  size_t off = (size_t)Q * (16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4 + 4);
+  size_t off = (size_t)Q * (16 + 16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4 + 4);
   off = (off + 15) & ~(size_t)15;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw + off);
   float4* az_smem = reinterpret_cast<float4*>(smem_raw + smem_front_bytes(Q));
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
 
   const long long t_cta0 = clock64();
   PassBuffers pb;
-  pb.qpt = qpt; pb.sel = selbuf; pb.qa = qabuf; pb.qw = qwbuf; pb.qref = qrefbuf; pb.qref2 = qref2buf; pb.qccr = qccrbuf; pb.wl = wlbuf; pb.key = key; pb.pos = posbuf; pb.azS = nullptr; pb.azC = nullptr;
+  pb.qpt = qpt; pb.sel = selbuf; pb.qa = qabuf; pb.qw = qwbuf; pb.qref = qrefbuf; pb.qref2 = qref2buf; pb.qext = qextbuf; pb.qccr = qccrbuf; pb.wl = wlbuf; pb.key = key; pb.pos = posbuf; pb.azS = nullptr; pb.azC = nullptr;
 
   for (;;) {
     if (tid == 0) { sm.scan = atomicAdd(bv.work_counter, 1); sm.tlast = clock64(); }
@@ -998,9 +999,10 @@ int map_pass(lins_ctx* ctx, int nc, int ns, const float* T, bool dense, float* A
   int slices[2], slice_len[2];
   size_t part = 0;
   for (int k = 0; k < 2; ++k) {
-    // enough (query block, map slice) pairs to cover the SMs twice; a slice is at least one tile
-    int S = qb[k] > 0 ? (2 * ctx->sm_count + qb[k] - 1) / qb[k] : 1;
-    S = std::max(1, std::min(S, std::min(64, (nm[k] + kTile - 1) / kTile)));
+    // enough (query block, map slice) pairs for ~8 CTAs per SM (the scan is latency bound: profiles/r01_map_*); a slice
+    // is at least 256 map points
+    int S = qb[k] > 0 ? (8 * ctx->sm_count + qb[k] - 1) / qb[k] : 1;
+    S = std::max(1, std::min(S, std::min(64, (nm[k] + 255) / 256)));
     slices[k] = S;
     slice_len[k] = std::max(1, (nm[k] + S - 1) / S);
     part = std::max(part, (size_t)nq[k] * S * 5);
