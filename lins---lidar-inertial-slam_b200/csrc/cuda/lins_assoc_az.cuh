@@ -18,13 +18,16 @@
 //   resolve like the reference's "first strictly smaller wins" loops; the 1-NN key is (distance bits, original
 //   index): lowest index among exact ties.
 //
-// Certificates.  Every search also returns how much room its answer has: the runner-up's distance (or the
-// distance bound of everything outside the window, whichever is smaller) minus the winner's, and the winner's
-// distance to the 5 m gate.  While the query has moved less than half of the smallest such slack since that
-// search (true distances change by at most the displacement), neither the argmin nor any gate decision can
-// change, so the stored answer is reused and the search is skipped.  Exact ties have slack 0 and are therefore
-// re-searched every iteration.  Windows are built for sqrt(U) + kCertMargin so the "outside" bound is not vacuous.
-// The closest point and the walks are certified separately (a new closest point always forces new walks).
+// Certificates.  Every search also returns its two front-runners (winner and runner-up slots) and a bound: the
+// distance every OTHER candidate exceeded at the search position (the third best distance, or the distance bound of
+// everything outside the window, whichever is smaller).  Later, one thread re-evaluates the two front-runners exactly;
+// if the winner still beats the runner-up (exact keys), is still inside the gate, and is closer than
+// bound - displacement (true distances change by at most the displacement), nothing else can have overtaken it: the
+// stored answer is reused and the search is skipped (cert_accepted).  A plain winner / runner-up margin cannot certify a
+// query that sits almost midway between two neighbouring points of a ring — the common case; this can.  Three-way
+// exact ties fail the test and are re-searched.  A search that found nothing within the gate keeps a plain slack
+// (cert_rejected).  Windows are built for sqrt(U) + kCertMargin so the "outside" bound is not vacuous.  The closest
+// point and the walks are certified separately (a new closest point always forces new walks).
 #pragma once
 #include "lins_kernels.cuh"
 

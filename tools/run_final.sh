@@ -5,4 +5,6 @@ md5sum lins---lidar-inertial-slam_b200/liblins_gpu.so | cut -c1-8 > gpurun_out/b
 (time timeout 120 python -u -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')") > gpurun_out/smoke.log 2>&1
 (time timeout 400 python -u bench.py --steps 12 --warmup 3) > gpurun_out/bench.log 2>&1
 (time timeout 300 python -u bench.py --impl reference --steps 2 --warmup 1) > gpurun_out/bench_ref.log 2>&1
-cat gpurun_out/build_id.txt; tail -n 3 gpurun_out/t1.log; tail -n 3 gpurun_out/smoke.log; tail -n 5 gpurun_out/bench.log | cut -c1-300; tail -n 4 gpurun_out/bench_ref.log | cut -c1-300
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_r01_d.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:lins_ieskf -s 4 -c 1 -o gpurun_out/prof_r01_d_fused python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/prof_d1.log 2>&1
+cat gpurun_out/build_id.txt; tail -n 3 gpurun_out/t1.log; tail -n 3 gpurun_out/smoke.log; tail -n 5 gpurun_out/bench.log | cut -c1-300; tail -n 4 gpurun_out/bench_ref.log | cut -c1-300; ls gpurun_out | tail -n 5
