@@ -10,16 +10,14 @@
 
 namespace lins_dev {
 
-// Probe-first search (lins_assoc_az.cuh: az_probe_window).  Measured on the VLP-16 workload: it pays for the closest-
-// point search of a scan's FIRST pass (every query is unseeded, all warps are busy, the phase is issue bound:
-// 176 K -> 104 K cycles per scan) and costs time everywhere else (later passes and the walks are bound by the latency
-// of a few lone searches, which a second scan only lengthens).
+// Probe-first search (lins_assoc_az.cuh: az_probe_window) is used for the closest-point search of a scan's FIRST pass
+// only.  Measured on the VLP-16 workload: there every query is unseeded, all warps are busy and the phase is issue
+// bound (176 K -> 104 K cycles per scan); in later passes and for the walks a search is a lone warp bound by latency,
+// which a second scan only lengthens (tried, slower).
 #ifndef LINS_SEARCH_DIAG
 #define LINS_SEARCH_DIAG 0
 #endif
 constexpr bool kSearchDiag = LINS_SEARCH_DIAG != 0;  // per-search cycle counters for tools/phase_profile.py
-constexpr bool kProbeNN = true;
-constexpr bool kProbeWalk = false;
 
 struct PassBuffers {
   float4* qpt;               // staged queries (x, y, z, intensity) of the current tile
@@ -93,48 +91,47 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
     }
     LINS_TICK(2);
     // ---- A2: de-skew ---------------------------------------------------------------------------------------------
+    // ... fused with phase P1 of the association (same thread-per-query mapping, P1 touches only its own query's
+    // state and the read-only index): per-query level -2 everything certified, -3 closest point certified (walks
+    // only), >= 0 full search (= window), -1 cannot match.  The work-list counters were reset after the previous pass.
+    const bool p1_here = search && fast;
     for (int i = threadIdx.x; i < nq; i += kThreads) {
-      pb.sel[i] = transform_to_start(pb.qpt[i], sm, kp.scan_period);
+      const float4 s = transform_to_start(pb.qpt[i], sm, kp.scan_period);
+      pb.sel[i] = s;
       pb.key[i] = kKeyMax;
+      if (!p1_here) continue;
+      const bool surf = i < nsT;
+      float4 qa = make_float4(0.f, 0.f, -1.f, 0.f);
+      if (seeded) {  // certificates (lins_assoc_az.cuh: cert_accepted / cert_rejected): the stored answers still hold
+        const float4 r1 = pb.qref[i], r2 = pb.qref2[i], ex = pb.qext[i];
+        const AzIndex& ixq = surf ? ixS : ixC;
+        const unsigned nearbits = __float_as_uint(nearf);
+        const float moved1 = sqrtf(sqdist_f32(s.x, s.y, s.z, r1.x, r1.y, r1.z));
+        const int w1s = pb.pos[3 * i];
+        const bool ok1 = w1s >= 0 ? cert_accepted<false>(ixq, s, w1s, __float_as_int(ex.y), r1.w, moved1, nearbits, 0) : cert_rejected(r1.w, moved1);
+        bool ok2 = false;
+        const int ccr0 = pb.qccr[i];
+        if (ok1 && ccr0 >= 0) {  // (the walks' candidate sets are defined by the closest point: only meaningful while it stands)
+          const int c0 = ccr0 & 0x00ffffff;
+          const float moved2 = sqrtf(sqdist_f32(s.x, s.y, s.z, r2.x, r2.y, r2.z));
+          const int w2s = pb.pos[3 * i + 1], w3s = pb.pos[3 * i + 2];
+          ok2 = w2s >= 0 ? cert_accepted<true>(ixq, s, w2s, __float_as_int(ex.z), r2.w, moved2, nearbits, c0) : cert_rejected(r2.w, moved2);
+          if (ok2 && surf) ok2 = w3s >= 0 ? cert_accepted<true>(ixq, s, w3s, __float_as_int(ex.w), ex.x, moved2, nearbits, c0) : cert_rejected(ex.x, moved2);
+        }
+        if (ok1 && (ok2 || ccr0 < 0)) { pb.qw[i] = make_int4(-2, 0, 0, 0); continue; }
+        if (ok1) { az_polar(s, qa); pb.qa[i] = qa; pb.qw[i] = make_int4(-3, 0, 0, 0); continue; }
+      }
+      const int w1 = az_prepare_nn(surf ? ixS : ixC, s, nearf, seeded ? pb.pos[3 * i] : -1, qa);
+      pb.qa[i] = qa;
+      pb.qw[i] = make_int4(w1, 0, 0, 0);
+      pb.wl[atomicAdd(&sm.wl_n[0], 1)] = i;  // (list order does not matter: every query's result goes to its own slot)
+      if (bv.timers && w1 >= 0) atomicAdd(&sm.dbg[0], w1 & 0xffff);
     }
-    if (threadIdx.x == kThreads - 1) { sm.wl_n[0] = 0; sm.wl_n[1] = 0; sm.wl_head[0] = 0; sm.wl_head[1] = 0; sm.dbg[0] = 0; sm.dbg[1] = 0; }
     __syncthreads();
     LINS_TICK(3);
     if (search && fast) {
-      // ---- A3/A4 fast path, four short phases.  Scalar preparation (atan2f, asinf, bounds) runs one THREAD per
-      // query so that all queries proceed in parallel; the memory scans run one WARP per query.
-      // per-query level: -2 everything certified, -3 closest point certified (walks only), >= 0 full search (= window),
-      // -1 cannot match
-      for (int i = threadIdx.x; i < nq; i += kThreads) {  // P1
-        const float4 s = pb.sel[i];
-        const bool surf = i < nsT;
-        float4 qa = make_float4(0.f, 0.f, -1.f, 0.f);
-        if (seeded) {  // certificates (lins_assoc_az.cuh: cert_accepted / cert_rejected): the stored answers still hold
-          const float4 r1 = pb.qref[i], r2 = pb.qref2[i], ex = pb.qext[i];
-          const AzIndex& ixq = surf ? ixS : ixC;
-          const unsigned nearbits = __float_as_uint(nearf);
-          const float moved1 = sqrtf(sqdist_f32(s.x, s.y, s.z, r1.x, r1.y, r1.z));
-          const int w1s = pb.pos[3 * i];
-          const bool ok1 = w1s >= 0 ? cert_accepted<false>(ixq, s, w1s, __float_as_int(ex.y), r1.w, moved1, nearbits, 0) : cert_rejected(r1.w, moved1);
-          bool ok2 = false;
-          const int ccr0 = pb.qccr[i];
-          if (ok1 && ccr0 >= 0) {  // (the walks' candidate sets are defined by the closest point: only meaningful while it stands)
-            const int c0 = ccr0 & 0x00ffffff;
-            const float moved2 = sqrtf(sqdist_f32(s.x, s.y, s.z, r2.x, r2.y, r2.z));
-            const int w2s = pb.pos[3 * i + 1], w3s = pb.pos[3 * i + 2];
-            ok2 = w2s >= 0 ? cert_accepted<true>(ixq, s, w2s, __float_as_int(ex.z), r2.w, moved2, nearbits, c0) : cert_rejected(r2.w, moved2);
-            if (ok2 && surf) ok2 = w3s >= 0 ? cert_accepted<true>(ixq, s, w3s, __float_as_int(ex.w), ex.x, moved2, nearbits, c0) : cert_rejected(ex.x, moved2);
-          }
-          if (ok1 && (ok2 || ccr0 < 0)) { pb.qw[i] = make_int4(-2, 0, 0, 0); continue; }
-          if (ok1) { az_polar(s, qa); pb.qa[i] = qa; pb.qw[i] = make_int4(-3, 0, 0, 0); continue; }
-        }
-        const int w1 = az_prepare_nn(surf ? ixS : ixC, s, nearf, seeded ? pb.pos[3 * i] : -1, qa);
-        pb.qa[i] = qa;
-        pb.qw[i] = make_int4(w1, 0, 0, 0);
-        pb.wl[atomicAdd(&sm.wl_n[0], 1)] = i;  // (list order does not matter: every query's result goes to its own slot)
-        if (bv.timers && w1 >= 0) atomicAdd(&sm.dbg[0], w1 & 0xffff);
-      }
-      __syncthreads();
+      // ---- A3/A4 fast path.  Scalar preparation (certificates, atan2f, asinf, bounds: P1 above, P3 below) runs one
+      // THREAD per query so that all queries proceed in parallel; the memory scans (P2, P4) run one WARP per query.
       if (bv.timers && threadIdx.x == 0) {
         atomicAdd((unsigned long long*)&bv.timers[10], (unsigned long long)sm.wl_n[0]);
         atomicAdd((unsigned long long*)&bv.timers[12], (unsigned long long)sm.dbg[0]);
@@ -163,7 +160,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         const float4 s = pb.sel[i];
         float4 qa = pb.qa[i];
         if (w1 >= 0) {
-          const int wp = first_pass_of_scan ? az_probe_window<kProbeNN>(ix, qa, w1) : -1;
+          const int wp = first_pass_of_scan ? az_probe_window(ix, qa, w1) : -1;
           if (wp >= 0) {  // wide window (no usable previous answer): probe first, then search inside the implied window
             const Top3 pr = az_scan_nn(ix, s, wp);
             if (pr.p1 >= 0) {
@@ -178,7 +175,7 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
           const float d1 = __uint_as_float((unsigned)(k1 >> 32));
           const bool acc1 = k1 != kKeyMax && p1 >= 0 && (double)d1 < kp.nearest_sq;
           // accepted: what everything but the two front-runners exceeded; else the slack of "nothing within the gate"
-          const float bound1 = w1 < 0 ? -1.f : acc1 ? cert_bound(top.d3, qa.w) : search_slack((unsigned)(k1 >> 32), (unsigned)(top.k2 >> 32), qa.w, gate, false);
+          const float bound1 = w1 < 0 ? -1.f : acc1 ? cert_bound(top.d3, qa.w) : rejected_slack((unsigned)(k1 >> 32), qa.w, gate);
           pb.qref[i] = make_float4(s.x, s.y, s.z, bound1);
           pb.qext[i].y = __int_as_float(acc1 ? top.p2 : -1);
           pb.pos[3 * i] = acc1 ? p1 : -1;
@@ -244,29 +241,9 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
         const long long t_s0 = (diag && lane == 0) ? clock64() : 0;
         const bool surf = i < nsT;
         const int gq = q0 + i;
-        float2 B = reinterpret_cast<const float2*>(pb.key)[i];
-        int w2 = w.y, w3 = w.z;
+        const float2 B = reinterpret_cast<const float2*>(pb.key)[i];
+        const int w2 = w.y, w3 = w.z;
         const float4 s = pb.sel[i];
-        {  // wide windows (no usable previous answer): probe a small window first and re-window from what it finds
-          const float4 qa = pb.qa[i];
-          const int wide = max(w2 & 0xffff, surf ? (w3 & 0xffff) : 0);
-          const int wp = az_probe_window<kProbeWalk>(surf ? ixS : ixC, qa, wide);
-          if (wp >= 0) {
-            const int c = w.w & 0x00ffffff, cr = (int)((unsigned)w.w >> 24);
-            const int sd2 = seeded ? pb.pos[3 * i + 1] : -1, sd3 = seeded ? pb.pos[3 * i + 2] : -1;
-            float b2, b3;
-            int pw2, pw3;
-            if (surf) {
-              az_prepare_walk<true>(ixS, s, qa, c, cr, -1, -1, fwdS, kProbeSq, pw2, pw3, b2, b3);
-              const WalkOut pr = az_scan_walk<true>(ixS, s, w.w, pw2, pw3, fwdS, nearf, b2, b3);
-              az_prepare_walk<true>(ixS, s, qa, c, cr, sd2, sd3, fwdS, nearf, w2, w3, B.x, B.y, pr.pos2, pr.pos3);
-            } else {
-              az_prepare_walk<false>(ixC, s, qa, c, cr, -1, -1, fwdC, kProbeSq, pw2, pw3, b2, b3);
-              const WalkOut pr = az_scan_walk<false>(ixC, s, w.w, pw2, pw3, fwdC, nearf, b2, b3);
-              az_prepare_walk<false>(ixC, s, qa, c, cr, sd2, sd3, fwdC, nearf, w2, w3, B.x, B.y, pr.pos2, pr.pos3);
-            }
-          }
-        }
         const WalkOut wo = surf ? az_scan_walk<true>(ixS, s, w.w, w2, w3, fwdS, nearf, B.x, B.y) : az_scan_walk<false>(ixC, s, w.w, w2, w3, fwdC, nearf, B.x, B.y);
         const int i2 = wo.i2, i3 = wo.i3;
         if (lane == 0) {
@@ -326,6 +303,8 @@ __device__ void association_pass(Smem& sm, const BatchView& bv, const KParams& k
     }
     __syncthreads();
     LINS_TICK_F(5, 29, first_pass_of_scan);
+    // the searches of this pass are over: reset the work lists for the next pass (whose P1 is fused with the de-skew)
+    if (threadIdx.x == kThreads - 1) { sm.wl_n[0] = 0; sm.wl_n[1] = 0; sm.wl_head[0] = 0; sm.wl_head[1] = 0; sm.dbg[0] = 0; sm.dbg[1] = 0; }
     // ---- A5/A6 residuals + A7-A9 fold ------------------------------------------------------------------------------
     // tripod points: fast path -> slots of the sorted copies; otherwise original indices into the walk clouds.
     // (fast path with several tiles on a non-search iteration falls back to original indices, see above)

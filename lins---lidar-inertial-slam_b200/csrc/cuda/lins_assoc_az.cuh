@@ -134,13 +134,12 @@ __device__ __forceinline__ int pack_window(int blo, int nbins) { return (blo << 
 constexpr float kCertMargin = LINS_CERT_MARGIN;  // metres added to every search radius so that certificates have room
 // bound used to build a window: (sqrt(U) + margin)^2
 __device__ __forceinline__ float widen(float U) { const float r = sqrtf(U) + kCertMargin; return r * r; }
-// slack (metres) of one search: winner / runner-up as f32 squared-distance BITS (0xffffffff = none), Bout = distance
-// bound of everything not examined, gate = sqrt(NEAREST_FEATURE_SEARCH_SQ_DIST).  Negative = cannot be certified.
-__device__ __forceinline__ float search_slack(unsigned best_bits, unsigned second_bits, float Bout, float gate, bool accepted) {
+// slack (metres) of a search that found nothing within the gate: how far its best candidate (f32 squared-distance
+// BITS, 0xffffffff = none) or everything not examined (Bout) lies beyond gate = sqrt(NEAREST_FEATURE_SEARCH_SQ_DIST).
+// Negative = cannot be certified.
+__device__ __forceinline__ float rejected_slack(unsigned best_bits, float Bout, float gate) {
   const float db = best_bits >= 0x7f800000u ? Bout : fminf(sqrtf(__uint_as_float(best_bits)), Bout);
-  if (!accepted) return db - gate * 1.00001f;                      // stays "nothing within the gate"
-  const float ds = second_bits >= 0x7f800000u ? Bout : fminf(sqrtf(__uint_as_float(second_bits)), Bout);
-  return fminf(ds - db, gate * 0.99999f - db);                     // stays the winner, stays inside the gate
+  return db - gate * 1.00001f;
 }
 
 // ---- phase P1 (one THREAD per query): azimuth, range, bound and window of the closest-point search ------------
@@ -177,27 +176,15 @@ __device__ __forceinline__ int az_prepare_nn(const AzIndex& ix, const float4 s, 
 // than the window of this radius first scans the small window; the best candidate found there is a real target,
 // so its distance is a valid upper bound and the exact search runs inside the (much smaller) window it implies.
 constexpr float kProbeSq = 0.25f;  // (0.5 m)^2
-template <bool ENABLED>
 __device__ __forceinline__ int az_probe_window(const AzIndex& ix, const float4 qa, int full_window) {
-  if (!ENABLED) return -1;
   int blo, nbins;
   az_window(ix.nb, qa.x, az_halfwidth(kProbeSq, qa.y), blo, nbins);
   return (full_window & 0xffff) > 2 * nbins + 4 ? pack_window(blo, nbins) : -1;
 }
 
 // ---- phase P2 (one WARP per query): exact 1-NN over all rings inside the window ---------------------------------
-// LPR lanes share one ring; two candidates per lane are in flight per trip (the scan is latency bound).
-// Branch-free bookkeeping of (best key, its slot, runner-up distance): a lone warp runs these scans with nothing to
-// hide latency behind, so the loop body is straight-line code with independent chains (four candidates per lane per
-// trip, reduced as a small tournament) instead of data-dependent branches.
-//   keep(a, b): a <- min(a, b) (with its slot), returns the distance bits of the loser
-__device__ __forceinline__ unsigned keep_min(unsigned long long& a, int& pa, unsigned long long b, int pb) {
-  const bool lt = b < a;
-  const unsigned loser = (unsigned)((lt ? a : b) >> 32);
-  a = lt ? b : a;
-  pa = lt ? pb : pa;
-  return loser;
-}
+// LPR lanes share one ring; four candidates per lane are in flight per trip.  A lone warp runs these scans with
+// nothing to hide latency behind, so the bookkeeping is branch-free straight-line code.
 // The two smallest keys seen so far with their slots, and the distance bits of the third.  Certificates built on the
 // third distance survive a near-tie between the two front-runners (the common reason an answer could not be certified:
 // a query almost equidistant from two neighbouring points of a ring): those two are simply re-evaluated exactly.
@@ -328,18 +315,13 @@ __device__ __forceinline__ float walk_seed_bound(const AzIndex& ix, const float4
   }
   return U;
 }
-// Uinit = NEAREST_FEATURE_SEARCH_SQ_DIST for a real search (nothing beyond the gate is accepted), kProbeSq for a probe
+// Uinit = NEAREST_FEATURE_SEARCH_SQ_DIST: nothing beyond the gate is accepted
 template <bool SURF>
 __device__ __forceinline__ void az_prepare_walk(const AzIndex& ix, const float4 s, const float4 qa, int c, int cr, int seed2,
-                                                int seed3, int fwdBound, float Uinit, int& w2, int& w3, float& B2, float& B3,
-                                                int seed2b = -1, int seed3b = -1) {
-  // bounds from the previous answers (and / or a probe's answers)
-  float U2 = walk_seed_bound<SURF, true>(ix, s, seed2, c, cr, fwdBound, Uinit), U3 = Uinit;
-  U2 = walk_seed_bound<SURF, true>(ix, s, seed2b, c, cr, fwdBound, U2);
-  if (SURF) {
-    U3 = walk_seed_bound<SURF, false>(ix, s, seed3, c, cr, fwdBound, U3);
-    U3 = walk_seed_bound<SURF, false>(ix, s, seed3b, c, cr, fwdBound, U3);
-  }
+                                                int seed3, int fwdBound, float Uinit, int& w2, int& w3, float& B2, float& B3) {
+  // bounds from the previous answers
+  const float U2 = walk_seed_bound<SURF, true>(ix, s, seed2, c, cr, fwdBound, Uinit);
+  const float U3 = SURF ? walk_seed_bound<SURF, false>(ix, s, seed3, c, cr, fwdBound, Uinit) : Uinit;
   int blo, nbins;
   const float Uw2 = widen(U2);
   az_window(ix.nb, qa.x, az_halfwidth(Uw2, qa.y), blo, nbins);
@@ -405,14 +387,14 @@ __device__ __forceinline__ WalkOut az_scan_walk_t(const AzIndex& ix, const float
   neutral.init();
   WalkOut o;
   // accepted (within the gate): bound = distance everything but the two front-runners exceeded; otherwise the slack
-  // of "still nothing within the gate" (search_slack)
+  // of "still nothing within the gate" (rejected_slack)
   auto finish = [&](Top3 t, float Bout, int& idx, int& pos, int& run, float& bound) {
     warp_top3(t);
     const bool ok = (unsigned)(t.k1 >> 32) < nearbits && t.p1 >= 0;
     idx = ok ? order_decode((unsigned)(t.k1 & 0xffffffffu)) : -1;
     pos = ok ? t.p1 : -1;
     run = ok ? t.p2 : -1;
-    bound = ok ? cert_bound(t.d3, Bout) : search_slack((unsigned)(t.k1 >> 32), (unsigned)(t.k2 >> 32), Bout, gate, false);
+    bound = ok ? cert_bound(t.d3, Bout) : rejected_slack((unsigned)(t.k1 >> 32), Bout, gate);
   };
   finish(mine2 ? top : neutral, B2, o.i2, o.pos2, o.run2, o.bound2);
   if (SURF) finish(mine2 ? neutral : top, B3, o.i3, o.pos3, o.run3, o.bound3);

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
   if (tid == 0) {
     mbar_init(&sm.mbar, 1);
     sm.phase = 0;
+    sm.wl_n[0] = 0; sm.wl_n[1] = 0; sm.wl_head[0] = 0; sm.wl_head[1] = 0; sm.dbg[0] = 0; sm.dbg[1] = 0;  // (reset after every pass)
     fence_mbar_init();
   }
   __syncthreads();
