@@ -148,3 +148,71 @@ int main() {
     assert np.allclose(E, np.linalg.eigvalsh(A), rtol=1e-10)
     assert np.allclose(Ai, np.linalg.inv(A), rtol=1e-8)
     assert abs(rest[0] - 0.1) < 1e-3 and abs(rest[1] - 0.1) < 1e-12 and rest[2] > 0 and rest[3] == 0
+
+
+def test_host_pool_and_map_host_code(tmp_path):
+    """More of the product's host C++ (csrc/host): the persistent worker pool (every run executes fn on exactly n
+    threads and returns only when all are done, across many generations and changing n) and the row-F2 host pieces
+    (lins_cv_small.hpp / lins_map_host.hpp: cv::eigen / cv::solve restatements, the LM step) against OpenCV / numpy."""
+    import subprocess
+
+    host = os.path.join(ROOT, "lins---lidar-inertial-slam_b200", "csrc", "host")
+    src = tmp_path / "p.cpp"
+    src.write_text(r'''
+#include <atomic>
+#include <cstdio>
+#include "host_pool.hpp"
+#include "lins_map_host.hpp"
+int main() {
+  HostPool pool;
+  long total = 0;
+  for (int gen = 0; gen < 400; ++gen) {
+    const int n = 1 + (gen * 7) % 13;
+    std::atomic<int> calls(0), work(0);
+    std::atomic<size_t> next(0);
+    pool.run(n, [&] { ++calls; for (;;) { size_t i = next.fetch_add(1); if (i >= 1000) break; ++work; } });
+    if (calls.load() != n || work.load() != 1000) { printf("BAD gen %d calls %d work %d\n", gen, calls.load(), work.load()); return 1; }
+    total += work.load();
+  }
+  printf("pool %ld\n", total);
+  // cv small kernels on a fixed input (compared with cv2 / numpy by the caller)
+  float A[9] = {2.0f, 0.3f, -0.1f, 0.3f, 1.0f, 0.2f, -0.1f, 0.2f, 0.5f}, W[3], V[9];
+  lins_cv::jacobi_eigen<3>(A, W, V);
+  for (float w : W) printf("%.9g ", w);
+  for (float v : V) printf("%.9g ", v);
+  float Q[15] = {1.0f, 2.0f, 0.5f, 1.1f, 2.1f, 0.4f, 0.9f, 1.8f, 0.7f, 1.3f, 2.2f, 0.45f, 0.8f, 1.9f, 0.55f}, b[5] = {-1, -1, -1, -1, -1};
+  const bool ok = lins_cv::qr_solve<5, 3>(Q, b);
+  printf("%d %.9g %.9g %.9g ", (int)ok, b[0], b[1], b[2]);
+  // one LM step on a well-conditioned system
+  float AtA[36], AtB[6], T[6] = {0.01f, -0.02f, 0.03f, 1.f, 2.f, 3.f};
+  for (int i = 0; i < 6; ++i) { for (int j = 0; j < 6; ++j) AtA[i * 6 + j] = (i == j ? 500.f + 10.f * i : 3.f / (1 + i + j)); AtB[i] = 0.5f * (i + 1); }
+  lins::mapping::LmState st;
+  float dR, dT;
+  const bool conv = lins::mapping::lm_step(AtA, AtB, 0, T, st, dR, dT);
+  printf("%d %d %.9g %.9g ", (int)conv, (int)st.isDegenerate, dR, dT);
+  for (float t : T) printf("%.9g ", t);
+  return 0;
+}''')
+    exe = tmp_path / "p"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", host, "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], timeout=120).decode().split()
+    assert out[0] == "pool" and int(out[1]) == 400 * 1000
+    v = np.array(out[2:], dtype=np.float64)
+    A = np.array([[2.0, 0.3, -0.1], [0.3, 1.0, 0.2], [-0.1, 0.2, 0.5]], np.float32)
+    W, V = v[:3], v[3:12].reshape(3, 3)
+    assert np.allclose(W, np.linalg.eigvalsh(A.astype(np.float64))[::-1], rtol=1e-5)
+    assert np.allclose(np.abs(V @ A @ V.T - np.diag(W)).max(), 0, atol=1e-5)
+    Q = np.array([1.0, 2.0, 0.5, 1.1, 2.1, 0.4, 0.9, 1.8, 0.7, 1.3, 2.2, 0.45, 0.8, 1.9, 0.55], np.float32).reshape(5, 3)
+    assert int(v[12]) == 1 and np.allclose(v[13:16], np.linalg.lstsq(Q.astype(np.float64), -np.ones(5), rcond=None)[0], rtol=2e-4)
+    AtA = np.array([[500.0 + 10 * i if i == j else 3.0 / (1 + i + j) for j in range(6)] for i in range(6)])
+    x = np.linalg.solve(AtA, 0.5 * np.arange(1, 7))
+    T0 = np.array([0.01, -0.02, 0.03, 1, 2, 3])
+    assert int(v[17]) == 0 and np.allclose(v[20:26], T0 + x, rtol=1e-5)
+    try:  # where the real OpenCV is importable the f32 kernels are bit-identical to it
+        import cv2
+        _, w, vv = cv2.eigen(A)
+        assert np.array_equal(w.ravel(), W.astype(np.float32)) and np.array_equal(vv, V.astype(np.float32))
+        _, xq = cv2.solve(Q, -np.ones((5, 1), np.float32), flags=cv2.DECOMP_QR)
+        assert np.array_equal(xq.ravel(), v[13:16].astype(np.float32))
+    except ImportError:
+        pass
