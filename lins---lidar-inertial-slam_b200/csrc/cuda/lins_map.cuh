@@ -191,15 +191,17 @@ __global__ void __launch_bounds__(kFitThreads) lins_map_fit_kernel(const float4*
   int nsel = 0;
   if (qi < n_q) {
     // merge the slices' sorted lists: slices are ascending index ranges, so "strictly smaller displaces" keeps the
-    // lower index in front among equal distances
+    // lower index in front among equal distances.  A list is ascending, so it is left at its first entry that does
+    // not beat the current fifth best (most slices contribute nothing).
     Top5 t;
     t.init();
     for (int s = 0; s < n_slices; ++s) {
       const size_t o = ((size_t)qi * n_slices + s) * 5;
-#pragma unroll
       for (int k = 0; k < 5; ++k) {
         const int idx = part_i[o + k];
-        if (idx >= 0) t.insert(part_d[o + k], idx);
+        const float dk = part_d[o + k];
+        if (idx < 0 || !(dk < t.d[4])) break;
+        t.insert(dk, idx);
       }
     }
     const float4 po = __ldg(&q[qi]);
