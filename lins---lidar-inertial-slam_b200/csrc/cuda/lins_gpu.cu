@@ -46,7 +46,7 @@ __host__ __device__ inline size_t smem_bytes_for(int qtile, int cap_s, int cap_c
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_constant__ BatchView bv,
+__global__ void __launch_bounds__(kThreads, kMinCtas) lins_ieskf_kernel(const __grid_constant__ BatchView bv,
                                                               const __grid_constant__ KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int Q = bv.qtile;
@@ -213,8 +213,8 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
       // Joseph form with the LAST iteration's K, H, R (:595-596), all through the 6x6 system:
       //   K H = U E_c^T,  U = P[:,c] M^-1 A6 ;   K R K^T = sig2 U V^T,  V = P[:,c] M^-1
       form_M6(sm, sig2, tid, kThreads);
-      if (tid >= 64 && tid < 64 + 72) {  // right-hand sides [A6 | I6]
-        const int e = tid - 64, a = e / 12, c = e % 12;
+      for (int e = tid; e < 72; e += kThreads) {  // right-hand sides [A6 | I6]
+        const int a = e / 12, c = e % 12;
         sm.X6[e] = c < 6 ? sm.A6[a * 6 + c] : (a == c - 6 ? 1.0 : 0.0);
       }
       __syncthreads();
@@ -223,8 +223,8 @@ __global__ void __launch_bounds__(kThreads, 1) lins_ieskf_kernel(const __grid_co
         if (!ok) for (int e = lane; e < 72; e += 32) sm.X6[e] = __longlong_as_double(0x7ff8000000000000ll);
       }
       __syncthreads();
-      if (tid < 216) {
-        const int which = tid / 108, e = tid % 108, a = e / 6, c = e % 6;
+      for (int t = tid; t < 216; t += kThreads) {
+        const int which = t / 108, e = t % 108, a = e / 6, c = e % 6;
         double sacc = 0;
         for (int k = 0; k < 6; ++k) sacc += sm.P[a * 18 + col6(k)] * sm.X6[k * 12 + c + 6 * which];
         (which ? sm.V : sm.U)[e] = sacc;
@@ -446,6 +446,8 @@ struct lins_ctx {
   int map_ns = -1, map_nc = -1, tree_ns = -1, tree_nc = -1;
   bool tree_is_map = true;
   bool timers_on = false;
+  bool verbose = false;  // LINS_VERBOSE: print the launch configuration
+  int force_cap_s = -1, force_cap_c = -1;  // tuning knobs (LINS_CAP_S / LINS_CAP_C): upper limits of the shared-memory copies
   DevBuf<float4> tmp_pts;
   DevBuf<double> tmp_lin;
   PinBuf<float4> h_tmp;
@@ -521,6 +523,8 @@ template <int MODE>
 int launch_mode(lins_ctx* ctx, const BatchView& bv_in, const KParams& kp) {
   BatchView bv = bv_in;
   // keep the sorted target copies in shared memory when they fit; the corner copy is small and goes first
+  if (ctx->force_cap_s >= 0) bv.cap_s = std::min(bv.cap_s, ctx->force_cap_s);
+  if (ctx->force_cap_c >= 0) bv.cap_c = std::min(bv.cap_c, ctx->force_cap_c);
   if ((int)smem_bytes_for(bv.qtile, bv.cap_s, bv.cap_c) > ctx->max_smem_optin) {
     if ((int)smem_bytes_for(bv.qtile, 0, bv.cap_c) <= ctx->max_smem_optin) bv.cap_s = 0;
     else { bv.cap_s = 0; bv.cap_c = 0; }
@@ -533,6 +537,7 @@ int launch_mode(lins_ctx* ctx, const BatchView& bv_in, const KParams& kp) {
   if (per_sm < 1) per_sm = 1;
   int grid = std::min(bv.n_scans, ctx->sm_count * per_sm);
   if (grid < 1) grid = 1;
+  if (ctx->verbose) std::fprintf(stderr, "[lins_gpu] mode %d: %d threads, %zu B shared, %d CTA/SM, grid %d, cap_s %d cap_c %d qtile %d\n", MODE, kThreads, smem, per_sm, grid, bv.cap_s, bv.cap_c, bv.qtile);
   CK(cudaMemsetAsync(bv.work_counter, 0, sizeof(int), ctx->stream));
   lins_ieskf_kernel<MODE><<<grid, kThreads, smem, ctx->stream>>>(bv, kp);
   CK(cudaGetLastError());
@@ -671,6 +676,9 @@ int lins_gpu_create(const lins_params* params, int device, void* stream, lins_ct
   ctx->prm = *params;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  ctx->verbose = std::getenv("LINS_VERBOSE") != nullptr;
+  if (const char* e = std::getenv("LINS_CAP_S")) ctx->force_cap_s = std::atoi(e);
+  if (const char* e = std::getenv("LINS_CAP_C")) ctx->force_cap_c = std::atoi(e);
   if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
   else {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LINS_E_CUDA; }

@@ -20,7 +20,14 @@
 
 namespace lins_dev {
 
-constexpr int kThreads = 512;   // one 16-warp CTA per SM: the per-scan index + target copy take most of its shared memory (1024 threads = 64 regs: spills, measured 2x slower)
+#ifndef LINS_THREADS
+#define LINS_THREADS 512
+#endif
+#ifndef LINS_MIN_CTAS
+#define LINS_MIN_CTAS 1
+#endif
+constexpr int kThreads = LINS_THREADS;   // threads per CTA (one unit per CTA); LINS_MIN_CTAS = resident CTAs per SM the register budget is set for
+constexpr int kMinCtas = LINS_MIN_CTAS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kRingTab = 260;   // ring-start table: first target index with ring >= r, r = 0..259
 constexpr int kMaxRing = 256;   // rings outside [0, kMaxRing) or unsorted clouds take the sequential walk
