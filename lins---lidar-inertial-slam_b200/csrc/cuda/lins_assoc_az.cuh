@@ -2,9 +2,10 @@
 // reference lins/include/StateEstimator.hpp:844-915 and :970-1029).
 //
 // Per scan, once: the target cloud (ring-sorted, as the reference's extractFeatures emits it, :727-826) is
-// bucket-sorted on device by  ring * nb + azimuth_bin  into a packed copy (x, y, z, bits(original index)) that
-// lives in SHARED memory when it fits (the VLP-16 case) and in a global scratch otherwise; the bucket table
-// always lives in shared memory.  This replaces pcl::KdTreeFLANN::setInputCloud (:363-364, :1158-1159).
+// bucket-sorted on device by  ring * nb + azimuth_bin  into a packed copy (x, y, z, ring << 24 | original index) in
+// global memory (served from L1 / L2: a unit's copy is ~80 KB and only the slices inside a search window are
+// touched); the bucket table lives in shared memory (16-bit slots).  This replaces
+// pcl::KdTreeFLANN::setInputCloud (:363-364, :1158-1159).
 //
 // Per query, per iteration, one warp:
 //   every search is "the minimum of the exact f32 distance over a set of rings", and always comes with an upper
@@ -34,9 +35,8 @@
 namespace lins_dev {
 
 struct AzIndex {
-  const float4* pts;  // sorted copy (shared or global)
-  unsigned sbase;     // its shared-window address when it lives in shared memory, else 0
-  const int* bstart;  // [nrings * nb + 1], shared
+  const float4* pts;      // sorted copy (global)
+  const aztab_t* bstart;  // [nrings * nb + 1], shared
   int nb, nrings, T;
 };
 
@@ -52,14 +52,15 @@ __device__ __forceinline__ int az_bins_for(int nrings, int tab) {
   return tab / p2;
 }
 
-// counting sort of `src` (ring-sorted, rings validated by build_ring_table) into dst, table in bstart[0..TAB]
+// counting sort of `src` (ring-sorted, rings validated by check_ring_sorted, T < 65536) into dst; bucket starts ->
+// table[0..TAB].  cnt (TAB + 1 ints) and scan_tmp (kThreads ints) are CTA scratch.  Block-wide.
 template <int TAB>
-__device__ void az_build(const float4* __restrict__ src, int T, float4* dst, int* bstart, int* scan_tmp, int nb) {
-  for (int b = threadIdx.x; b <= TAB; b += kThreads) bstart[b] = 0;
+__device__ void az_build(const float4* __restrict__ src, int T, float4* dst, aztab_t* table, int* cnt, int* scan_tmp, int nb) {
+  for (int b = threadIdx.x; b <= TAB; b += kThreads) cnt[b] = 0;
   __syncthreads();
   for (int j = threadIdx.x; j < T; j += kThreads) {
     const float4 t = __ldg(&src[j]);
-    atomicAdd(&bstart[(int)t.w * nb + az_bin(t.x, t.y, nb)], 1);
+    atomicAdd(&cnt[(int)t.w * nb + az_bin(t.x, t.y, nb)], 1);
   }
   __syncthreads();
   constexpr int PER = TAB / kThreads;
@@ -67,7 +68,7 @@ __device__ void az_build(const float4* __restrict__ src, int T, float4* dst, int
   int loc[PER];
   int sum = 0;
 #pragma unroll
-  for (int k = 0; k < PER; ++k) { loc[k] = bstart[threadIdx.x * PER + k]; sum += loc[k]; }
+  for (int k = 0; k < PER; ++k) { loc[k] = cnt[threadIdx.x * PER + k]; sum += loc[k]; }
   scan_tmp[threadIdx.x] = sum;
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -82,28 +83,19 @@ __device__ void az_build(const float4* __restrict__ src, int T, float4* dst, int
     int run = incl - s;
 #pragma unroll
     for (int k = 0; k < PW; ++k) { const int v = part[k]; scan_tmp[threadIdx.x * PW + k] = run; run += v; }
-    if (threadIdx.x == 31) bstart[TAB] = incl;
+    if (threadIdx.x == 31) table[TAB] = (aztab_t)incl;
   }
   __syncthreads();
   {
     int run = scan_tmp[threadIdx.x];
 #pragma unroll
-    for (int k = 0; k < PER; ++k) { bstart[threadIdx.x * PER + k] = run; run += loc[k]; }
+    for (int k = 0; k < PER; ++k) { cnt[threadIdx.x * PER + k] = run; table[threadIdx.x * PER + k] = (aztab_t)run; run += loc[k]; }
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < T; j += kThreads) {  // scatter; the counters double as cursors
+  for (int j = threadIdx.x; j < T; j += kThreads) {  // scatter; the counters are the cursors now
     const float4 t = __ldg(&src[j]);
-    const int pos = atomicAdd(&bstart[(int)t.w * nb + az_bin(t.x, t.y, nb)], 1);
-    dst[pos] = make_float4(t.x, t.y, t.z, __int_as_float(((int)t.w << 24) | j));  // ring (8 bits) | original index (24 bits)
-  }
-  __syncthreads();
-  {  // cursors hold bucket ENDS == next bucket's start: shift back by one bucket
-    int prev[PER];
-#pragma unroll
-    for (int k = 0; k < PER; ++k) { const int b = threadIdx.x * PER + k; prev[k] = b == 0 ? 0 : bstart[b - 1]; }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PER; ++k) bstart[threadIdx.x * PER + k] = prev[k];
+    const int pos = atomicAdd(&cnt[(int)t.w * nb + az_bin(t.x, t.y, nb)], 1);
+    dst[pos] = make_float4(t.x, t.y, t.z, __int_as_float(((int)t.w << 24) | j));  // ring (7 bits) | original index (24 bits)
   }
   __syncthreads();
 }
@@ -232,26 +224,15 @@ __device__ __forceinline__ void warp_top3(Top3& t) {
 __device__ __forceinline__ float cert_bound(unsigned third_bits, float Bout) {
   return third_bits >= 0x7f800000u ? Bout : fminf(sqrtf(__uint_as_float(third_bits)), Bout);
 }
-// One slot of the sorted copy.  When the copy is in shared memory the load is an explicit ld.shared: the generic
-// load the compiler would otherwise emit has a longer latency and was scheduled one candidate at a time (all four
-// loads of a trip through the same registers), which left a lone warp waiting ~100 cycles per candidate.
-template <bool SMEM>
-__device__ __forceinline__ float4 ld_slot(const AzIndex& ix, int p) {
-  if (SMEM) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ix.sbase + 16u * (unsigned)p));
-    return v;
-  }
-  return ix.pts[p];
-}
-template <int LPR, bool SMEM>
+__device__ __forceinline__ float4 ld_slot(const AzIndex& ix, int p) { return ix.pts[p]; }
+template <int LPR>
 __device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4 s, int p, int pe, Top3& top) {
   for (; p < pe; p += 4 * LPR) {
     unsigned long long k[4];
     int q[4];
     float4 tt[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) tt[u] = ld_slot<SMEM>(ix, p + u * LPR < pe ? p + u * LPR : p);  // four loads in flight
+    for (int u = 0; u < 4; ++u) tt[u] = ld_slot(ix, p + u * LPR < pe ? p + u * LPR : p);  // four loads in flight
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int pu = p + u * LPR;
@@ -265,7 +246,7 @@ __device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4
     for (int u = 0; u < 4; ++u) top.insert(k[u], q[u]);
   }
 }
-template <int LPR, bool SMEM>
+template <int LPR>
 __device__ __forceinline__ Top3 az_scan_nn_t(const AzIndex& ix, const float4 s, int win, long long* tm = nullptr) {
   const int lane = threadIdx.x & 31;
   const int blo = win >> 16, nbins = win & 0xffff;
@@ -280,8 +261,8 @@ __device__ __forceinline__ Top3 az_scan_nn_t(const AzIndex& ix, const float4 s, 
     if (r < ix.nrings) {
       const int base = r * ix.nb;
       if (tm) { dbg_cand += max(0, (ix.bstart[base + e0] - ix.bstart[base + blo] - sub + LPR - 1) / LPR); if (e1 > 0) dbg_cand += max(0, (ix.bstart[base + e1] - ix.bstart[base] - sub + LPR - 1) / LPR); }
-      az_scan_nn_slice<LPR, SMEM>(ix, s, ix.bstart[base + blo] + sub, ix.bstart[base + e0], top);
-      if (e1 > 0) az_scan_nn_slice<LPR, SMEM>(ix, s, ix.bstart[base] + sub, ix.bstart[base + e1], top);
+      az_scan_nn_slice<LPR>(ix, s, ix.bstart[base + blo] + sub, ix.bstart[base + e0], top);
+      if (e1 > 0) az_scan_nn_slice<LPR>(ix, s, ix.bstart[base] + sub, ix.bstart[base + e1], top);
     }
   }
   if (tm) { tm[0] = clock64(); tm[2] = __reduce_max_sync(0xffffffffu, (unsigned)dbg_cand); tm[3] = __reduce_add_sync(0xffffffffu, (unsigned)dbg_cand); }
@@ -292,14 +273,9 @@ __device__ __forceinline__ Top3 az_scan_nn_t(const AzIndex& ix, const float4 s, 
 }
 // -> the two nearest (key, slot) pairs and the third distance, over every ring inside the window
 __device__ __forceinline__ Top3 az_scan_nn(const AzIndex& ix, const float4 s, int win, long long* tm = nullptr) {
-  if (ix.sbase) {
-    if (ix.nrings <= 8) return az_scan_nn_t<4, true>(ix, s, win, tm);
-    if (ix.nrings <= 16) return az_scan_nn_t<2, true>(ix, s, win, tm);
-    return az_scan_nn_t<1, true>(ix, s, win, tm);
-  }
-  if (ix.nrings <= 8) return az_scan_nn_t<4, false>(ix, s, win, tm);
-  if (ix.nrings <= 16) return az_scan_nn_t<2, false>(ix, s, win, tm);
-  return az_scan_nn_t<1, false>(ix, s, win, tm);
+  if (ix.nrings <= 8) return az_scan_nn_t<4>(ix, s, win, tm);
+  if (ix.nrings <= 16) return az_scan_nn_t<2>(ix, s, win, tm);
+  return az_scan_nn_t<1>(ix, s, win, tm);
 }
 
 // ---- phase P3 (one THREAD per query): bound + window the walks of a query whose closest point is (c, cr) -------
@@ -342,8 +318,8 @@ struct WalkOut {  // per class: original index (-1 = none within the gate), slot
   int i2, i3, pos2, pos3, run2, run3;
   float bound2, bound3;
 };
-template <bool SURF, bool SMEM>
-__device__ __forceinline__ WalkOut az_scan_walk_t(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
+template <bool SURF>
+__device__ __forceinline__ WalkOut az_scan_walk(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
                                                 float B2, float B3) {
   const int lane = threadIdx.x & 31;
   const int c = ccr & 0x00ffffff, cr = (int)((unsigned)ccr >> 24);
@@ -365,7 +341,7 @@ __device__ __forceinline__ WalkOut az_scan_walk_t(const AzIndex& ix, const float
       for (p += sub; p < pe; p += 12) {  // two candidates in flight per lane
         float4 tt[2];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) tt[u] = ld_slot<SMEM>(ix, p + 6 * u < pe ? p + 6 * u : p);
+        for (int u = 0; u < 2; ++u) tt[u] = ld_slot(ix, p + 6 * u < pe ? p + 6 * u : p);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int pu = p + 6 * u;
@@ -400,13 +376,6 @@ __device__ __forceinline__ WalkOut az_scan_walk_t(const AzIndex& ix, const float
   if (SURF) finish(mine2 ? neutral : top, B3, o.i3, o.pos3, o.run3, o.bound3);
   else { o.i3 = -1; o.pos3 = -1; o.run3 = -1; o.bound3 = 0.f; }
   return o;
-}
-
-template <bool SURF>
-__device__ __forceinline__ WalkOut az_scan_walk(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
-                                                float B2, float B3) {
-  if (ix.sbase) return az_scan_walk_t<SURF, true>(ix, s, ccr, w2, w3, fwdBound, nearf, B2, B3);
-  return az_scan_walk_t<SURF, false>(ix, s, ccr, w2, w3, fwdBound, nearf, B2, B3);
 }
 
 // ---- certificates (phase P1, one THREAD per query) ------------------------------------------------------------------

@@ -33,58 +33,275 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------------------
 // dynamic shared memory layout:
-//   [qpt float4 x Q][sel float4 x Q][qa float4 x Q][qw int4 x Q][qref, qref2, qext float4 x Q][key u64 x Q][pos int x 3Q][qccr int x Q][wl int x Q][Smem][azS ..][azC ..]
-// cap_s / cap_c = points of the (ring, azimuth)-sorted target copies kept in shared memory (0: global scratch)
+//   [CtaMem][Smem x nslots][wacc f64 x nslots*nvw*28][wcnt int x nslots*nvw*2][per-query arrays x nslots*qtile]
+// per-query arrays (kQueryBytes per query): qpt, sel, qa, qw, qref, qref2, qext (16 B each), key (8), pos (12), qccr (4),
+// wl (4).  When even one slot does not fit shared memory they live in a per-CTA global scratch instead (bv.qscratch).
 // ---------------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t smem_front_bytes(int qtile) {
-  size_t b = (size_t)qtile * (16 + 16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4 + 4);
-  b = (b + 15) & ~(size_t)15;
-  return b + ((sizeof(Smem) + 15) & ~(size_t)15);
+constexpr size_t kQueryBytes = 16 * 7 + 8 + 12 + 4 + 4;
+__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t query_array_bytes(int nslots, int qtile) { return align16((size_t)nslots * qtile * kQueryBytes); }
+__host__ __device__ inline size_t smem_fixed_bytes(int nslots, int qtile) {
+  const size_t nvw = (size_t)nslots * (qtile / 32);
+  return align16(sizeof(CtaMem)) + (size_t)nslots * align16(sizeof(Smem)) + align16(nvw * kNAcc * sizeof(double)) + align16(nvw * 2 * sizeof(int));
 }
-__host__ __device__ inline size_t smem_bytes_for(int qtile, int cap_s, int cap_c) {
-  return smem_front_bytes(qtile) + 16 * ((size_t)cap_s + (size_t)cap_c) + 16;
+
+// prologue of a freshly claimed unit: prior -> shared, the search index (≙ kdtree*->setInputCloud,
+// StateEstimator.hpp:363-364 / :1158-1159) built on device, queries staged, first linearisation constants.  Block-wide.
+template <int MODE>
+__device__ void unit_prologue(CtaMem& cta, Smem& sm, const BatchView& bv, const KParams& kp, const PassBuffers& pb, int slot) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int scan = sm.scan;
+  if (tid < 20) { const double v = tid < 19 ? bv.state_in[(size_t)scan * 20 + tid] : 0.0; sm.prior[tid] = v; sm.lin[tid] = v; }
+  for (int e = tid; e < 108; e += kThreads) {  // P[:, c] (cov_in is column-major)
+    const int a = e / 6, c = e % 6;
+    sm.Pc[e] = bv.cov_in[(size_t)scan * 324 + col6(c) * 18 + a];
+  }
+  if (tid == 32) {
+    sm.flags[0] = sm.flags[1] = sm.flags[2] = sm.flags[3] = 0; sm.residualNorm = 1e6;
+    sm.cnt[0] = sm.cnt[1] = 0;
+    sm.iter = MODE == MODE_IESKF ? 0 : kp.iter0;
+    sm.fresh = 0; sm.finished = 0; sm.first_pass = 1; sm.pos_valid = 0; sm.pos_is_slot = 0;
+    sm.run = 1;
+    if (MODE == MODE_IESKF && kp.num_iter <= 0) { sm.run = 0; sm.finished = 1; cta.any_finished = 1; }
+    sm.qs0 = bv.qs_off[scan]; sm.ns = bv.qs_off[scan + 1] - sm.qs0;
+    sm.qc0 = bv.qc_off[scan]; sm.nc = bv.qc_off[scan + 1] - sm.qc0;
+    sm.ts0 = bv.ts_off[scan]; sm.Ts = bv.ts_off[scan + 1] - sm.ts0;
+    sm.tc0 = bv.tc_off[scan]; sm.Tc = bv.tc_off[scan + 1] - sm.tc0;
+  }
+  __syncthreads();
+  check_ring_sorted(bv.ts + sm.ts0, sm.Ts, &sm.sortedS);
+  check_ring_sorted(bv.tc + sm.tc0, sm.Tc, &sm.sortedC);
+  if (tid == 0) {
+    // slot payload = ring (7 bits) | index (24 bits); bucket tables hold 16-bit slots
+    const bool ok = sm.sortedS && sm.sortedC && bv.nn_s == nullptr && bv.nn_c == nullptr && sm.Ts < 65536 && sm.Tc < 65536;
+    sm.az_ok = ok ? 1 : 0;
+    sm.nringsS = ok && sm.Ts > 0 ? (int)bv.ts[sm.ts0 + sm.Ts - 1].w + 1 : 0;  // ring-sorted: the last point has the largest ring
+    sm.nringsC = ok && sm.Tc > 0 ? (int)bv.tc[sm.tc0 + sm.Tc - 1].w + 1 : 0;
+    sm.nbS = az_bins_for(sm.nringsS, kAzTabS);
+    sm.nbC = az_bins_for(sm.nringsC, kAzTabC);
+  }
+  __syncthreads();
+  if (sm.az_ok) {
+    az_build<kAzTabS>(bv.ts + sm.ts0, sm.Ts, bv.az_s + sm.ts0, sm.azTabS, cta.u.build_tab, cta.scan_tmp, sm.nbS);
+    az_build<kAzTabC>(bv.tc + sm.tc0, sm.Tc, bv.az_c + sm.tc0, sm.azTabC, cta.u.build_tab, cta.scan_tmp, sm.nbC);
+  }
+  // queries: staged once per unit — 1-D TMA (cp.async.bulk + mbarrier) into shared memory, plain copies into the scratch
+  float4* qdst = pb.qpt + (size_t)slot * bv.qtile;
+  if (bv.qscratch == nullptr) {
+    const uint32_t bytes = (uint32_t)(sm.ns + sm.nc) * 16u;
+    if (bytes > 0) {
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&cta.mbar, bytes);
+        if (sm.ns > 0) tma_load_1d(qdst, bv.qs + sm.qs0, (uint32_t)sm.ns * 16u, &cta.mbar);
+        if (sm.nc > 0) tma_load_1d(qdst + sm.ns, bv.qc + sm.qc0, (uint32_t)sm.nc * 16u, &cta.mbar);
+      }
+      const unsigned int ph = cta.phase;  // one mbarrier phase per staged unit
+      mbar_wait(&cta.mbar, ph & 1u);
+      __syncthreads();
+      if (tid == 0) cta.phase = ph + 1u;
+    }
+  } else {
+    for (int i = tid; i < sm.ns + sm.nc; i += kThreads) qdst[i] = i < sm.ns ? __ldg(bv.qs + sm.qs0 + i) : __ldg(bv.qc + sm.qc0 + i - sm.ns);
+  }
+  if (warp == 0) iter_consts_warp0(sm);
+  __syncthreads();
+}
+
+// The serial tail of one unit's iteration (StateEstimator.hpp:535-580), run by ONE warp: finish the reduction, 6x6 gain
+// system, update, convergence logic, and the constants of the unit's NEXT iteration.  The tails of the resident units
+// run side by side on different warps.
+__device__ void unit_tail(CtaMem& cta, Smem& sm, const BatchView& bv, const KParams& kp, const PassBuffers& pb, int slot, double sig2) {
+  const int lane = threadIdx.x & 31;
+  const int iter = sm.iter;
+  lins_report* rep = bv.reports ? bv.reports + sm.scan : nullptr;
+  const int nq = sm.ns + sm.nc;
+  finish_acc_warp0(sm, pb.wacc + (size_t)slot * pb.nvw * kNAcc, pb.wcnt + (size_t)slot * pb.nvw * 2, (nq + 31) >> 5);
+  build_A6_warp0(sm);
+  if (slot == 0) LINS_TICK(18);
+  if (lane < 6) {  // y = b6 + A6 d_c on the 6 structural rows
+    double y = sm.y6[lane];
+    for (int c = 0; c < 6; ++c) y += sm.A6[lane * 6 + c] * sm.dvec[col6(c)];
+    sm.X6[lane] = y;
+  }
+  form_M6(sm, sig2, lane, 32);
+  __syncwarp();
+  const bool ok = warp_lu_cols<6>(sm.M6, sm.X6, 1);  // z = M^-1 (b6 + A6 d_c)
+  __syncwarp();
+  if (slot == 0) LINS_TICK(19);
+  double u = 0.0;
+  if (lane < 18) {  // K (r + H d) = P[:,c] z
+    double kx = 0;
+    for (int c = 0; c < 6; ++c) kx += sm.Pc[lane * 6 + c] * sm.X6[c];
+    u = ok ? (-kx + sm.dvec[lane]) : __longlong_as_double(0x7ff8000000000000ll);
+  }
+  const bool hasNaN = __ballot_sync(0xffffffffu, u != u) != 0u;  // :553-558
+  if (u != u) u = 0.0;
+  if (lane < 18) sm.upd[lane] = u;
+  __syncwarp();
+  double nrm = 0.0;  // lane 0: ||update||^2 (sequential order), lane 1: ||residual||^2
+  if (lane == 0) for (int a = 0; a < 18; ++a) nrm += sm.upd[a] * sm.upd[a];
+  if (lane == 1) nrm = sm.acc[27];
+  nrm = sqrt(nrm);
+  const double un = __shfl_sync(0xffffffffu, nrm, 0), rnorm = __shfl_sync(0xffffffffu, nrm, 1);
+  if (slot == 0) LINS_TICK(21);
+  if (lane == 0) {
+    if (rep) {
+      rep->m_surf[iter] = sm.cnt[0]; rep->m_corner[iter] = sm.cnt[1];
+      rep->residual_norm[iter] = rnorm; rep->update_norm[iter] = un;
+    }
+    if (hasNaN) {  // :559-563
+      sm.flags[2] = 1; sm.flags[1] = 1; sm.flags[3] = 1;
+    } else if (rnorm > sm.residualNorm * 10) {  // :566-570
+      sm.flags[1] = 1; sm.flags[3] = 1;
+    } else {
+      box_plus(sm);  // :573
+      if (un <= 1e-2 && !kp.force_all_iters) { sm.flags[0] = 1; sm.flags[3] = 1; }  // :576-578
+      sm.residualNorm = rnorm;
+    }
+    const bool search = (iter % kp.icp_freq) == 0;
+    if (search) sm.pos_is_slot = sm.az_ok; else if (!sm.pos_valid) sm.pos_is_slot = 0;
+    sm.pos_valid = 1;
+    sm.first_pass = 0;
+    sm.iter = iter + 1;
+    if (sm.flags[3] || iter + 1 >= kp.num_iter) { sm.finished = 1; sm.run = 0; cta.any_finished = 1; }
+  }
+  __syncwarp();
+  if (slot == 0) LINS_TICK(23);
+  if (!sm.finished) iter_consts_warp0(sm);
+  if (slot == 0) LINS_TICK(25);
+}
+
+// exit of one finished unit: covariance + outputs (StateEstimator.hpp:585-599).  Block-wide.
+__device__ void unit_exit(CtaMem& cta, Smem& sm, const BatchView& bv, double sig2) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int scan = sm.scan, iters = sm.iter;
+  const bool diverged = sm.flags[1] != 0;
+  auto& ex = cta.u.ex;
+  if (!diverged && iters > 0) {
+    // Joseph form with the LAST iteration's K, H, R (:595-596), all through the 6x6 system:
+    //   K H = U E_c^T,  U = P[:,c] M^-1 A6 ;   K R K^T = sig2 U V^T,  V = P[:,c] M^-1
+    for (int e = tid; e < 324; e += kThreads) {
+      const int r = e / 18, c = e % 18;
+      ex.P[e] = bv.cov_in[(size_t)scan * 324 + c * 18 + r];
+    }
+    form_M6(sm, sig2, tid, kThreads);
+    for (int e = tid; e < 72; e += kThreads) {  // right-hand sides [A6 | I6]
+      const int a = e / 12, c = e % 12;
+      ex.X6[e] = c < 6 ? sm.A6[a * 6 + c] : (a == c - 6 ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const bool ok = warp_lu_cols<6>(sm.M6, ex.X6, 12);
+      if (!ok) for (int e = lane; e < 72; e += 32) ex.X6[e] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    __syncthreads();
+    for (int t = tid; t < 216; t += kThreads) {
+      const int which = t / 108, e = t % 108, a = e / 6, c = e % 6;
+      double sacc = 0;
+      for (int k = 0; k < 6; ++k) sacc += sm.Pc[a * 6 + k] * ex.X6[k * 12 + c + 6 * which];
+      (which ? ex.V : ex.U)[e] = sacc;
+    }
+    __syncthreads();
+    for (int e = tid; e < 324; e += kThreads) {  // X = (I - K H) P = P - U P[c,:]
+      const int i = e / 18, j = e % 18;
+      double sacc = ex.P[e];
+      for (int c = 0; c < 6; ++c) sacc -= ex.U[i * 6 + c] * ex.P[col6(c) * 18 + j];
+      ex.X[e] = sacc;
+    }
+    __syncthreads();
+    for (int e = tid; e < 324; e += kThreads) {  // P <- X (I - K H)^T + sig2 U V^T
+      const int i = e / 18, j = e % 18;
+      double sacc = ex.X[e], t = 0;
+      for (int c = 0; c < 6; ++c) { sacc -= ex.X[i * 18 + col6(c)] * ex.U[j * 6 + c]; t += ex.U[i * 6 + c] * ex.V[j * 6 + c]; }
+      ex.P[e] = sacc + t * sig2;
+    }
+    __syncthreads();
+  }
+  // state_out / cov_out
+  if (tid < 20) bv.state_out[(size_t)scan * 20 + tid] = diverged ? sm.prior[tid] : sm.lin[tid];
+  for (int e = tid; e < 324; e += kThreads) {
+    const int r = e / 18, c = e % 18;
+    double v;
+    if (diverged || iters == 0) v = bv.cov_in[(size_t)scan * 324 + c * 18 + r];
+    else v = 0.5 * (ex.P[r * 18 + c] + ex.P[c * 18 + r]);  // enforceSymmetry (:597)
+    bv.cov_out[(size_t)scan * 324 + c * 18 + r] = v;
+  }
+  if (tid == 0) {
+    lins_scan_result& o = bv.results[scan];
+    o.scan_id = scan;
+    o.iters = (uint16_t)iters;
+    o.flags = (uint16_t)((sm.flags[0] ? 1 : 0) | (sm.flags[1] ? 2 : 0) | (sm.flags[2] ? 4 : 0));
+    const double* st = diverged ? sm.prior : sm.lin;
+    o.pose[0] = st[0]; o.pose[1] = st[1]; o.pose[2] = st[2];
+    o.pose[3] = st[6]; o.pose[4] = st[7]; o.pose[5] = st[8]; o.pose[6] = st[9];
+    lins_report* rep = bv.reports ? bv.reports + scan : nullptr;
+    if (rep) { rep->iters = iters; rep->converged = sm.flags[0]; rep->diverged = sm.flags[1]; rep->has_nan = sm.flags[2]; }
+  }
+  __syncthreads();  // (ex is reused by the next finished unit / the next prologue)
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, kMinCtas) lins_ieskf_kernel(const __grid_constant__ BatchView bv,
-                                                              const __grid_constant__ KParams kp) {
+                                                                     const __grid_constant__ KParams kp) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int Q = bv.qtile;
-  float4* qpt = reinterpret_cast<float4*>(smem_raw);
-  float4* selbuf = qpt + Q;
-  float4* qabuf = selbuf + Q;
-  int4* qwbuf = reinterpret_cast<int4*>(qabuf + Q);
-  float4* qrefbuf = reinterpret_cast<float4*>(qwbuf + Q);
-  float4* qref2buf = qrefbuf + Q;
-  float4* qextbuf = qref2buf + Q;
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(qextbuf + Q);
-  int* posbuf = reinterpret_cast<int*>(key + Q);
-  int* qccrbuf = posbuf + 3 * Q;
-  int* wlbuf = qccrbuf + Q;
-  size_t off = (size_t)Q * (16 + 16 + 16 + 16 + 16 + 16 + 16 + 8 + 12 + 4 + 4);
-  off = (off + 15) & ~(size_t)15;
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw + off);
-  float4* az_smem = reinterpret_cast<float4*>(smem_raw + smem_front_bytes(Q));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = bv.nslots, Q = bv.qtile, NQ = S * Q;
+  CtaMem& cta = *reinterpret_cast<CtaMem*>(smem_raw);
+  Smem* slots = reinterpret_cast<Smem*>(smem_raw + align16(sizeof(CtaMem)));
+  const size_t slot_stride = align16(sizeof(Smem));
+  auto slot_at = [&](int s) -> Smem& { return *reinterpret_cast<Smem*>(reinterpret_cast<unsigned char*>(slots) + s * slot_stride); };
+  static_assert(sizeof(Smem) % 16 == 0, "slots are indexed as an array");
+  const size_t nvw_all = (size_t)S * (Q / 32);
+  unsigned char* p = smem_raw + align16(sizeof(CtaMem)) + S * slot_stride;
+  PassBuffers pb;
+  pb.nvw = Q / 32;
+  pb.wacc = reinterpret_cast<double*>(p); p += align16(nvw_all * kNAcc * sizeof(double));
+  pb.wcnt = reinterpret_cast<int*>(p); p += align16(nvw_all * 2 * sizeof(int));
+  unsigned char* qbase = bv.qscratch ? bv.qscratch + (size_t)blockIdx.x * bv.qscratch_stride : p;
+  pb.qpt = reinterpret_cast<float4*>(qbase);
+  pb.sel = pb.qpt + NQ;
+  pb.qa = pb.sel + NQ;
+  pb.qw = reinterpret_cast<int4*>(pb.qa + NQ);
+  pb.qref = reinterpret_cast<float4*>(pb.qw + NQ);
+  pb.qref2 = pb.qref + NQ;
+  pb.qext = pb.qref2 + NQ;
+  pb.key = reinterpret_cast<unsigned long long*>(pb.qext + NQ);
+  pb.pos = reinterpret_cast<int*>(pb.key + NQ);
+  pb.qccr = pb.pos + 3 * NQ;
+  pb.wl = pb.qccr + NQ;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const double sig2 = kp.lidar_std * kp.lidar_std;
+  (void)slot_at;
 
   if (tid == 0) {
-    mbar_init(&sm.mbar, 1);
-    sm.phase = 0;
-    sm.wl_n[0] = 0; sm.wl_n[1] = 0; sm.wl_head[0] = 0; sm.wl_head[1] = 0; sm.dbg[0] = 0; sm.dbg[1] = 0;  // (reset after every pass)
+    mbar_init(&cta.mbar, 1);
+    cta.phase = 0;
+    cta.wl_n[0] = 0; cta.wl_n[1] = 0; cta.wl_head[0] = 0; cta.wl_head[1] = 0; cta.dbg[0] = 0; cta.dbg[1] = 0;  // (reset after every pass)
+    cta.exhausted = 0; cta.any_finished = 0;
+    for (int s = 0; s < S; ++s) { slots[s].scan = -1; slots[s].fresh = 0; slots[s].run = 0; slots[s].finished = 0; }
     fence_mbar_init();
+    cta.tlast = clock64();
   }
   __syncthreads();
-
   const long long t_cta0 = clock64();
-  PassBuffers pb;
-  pb.qpt = qpt; pb.sel = selbuf; pb.qa = qabuf; pb.qw = qwbuf; pb.qref = qrefbuf; pb.qref2 = qref2buf; pb.qext = qextbuf; pb.qccr = qccrbuf; pb.wl = wlbuf; pb.key = key; pb.pos = posbuf; pb.azS = nullptr; pb.azC = nullptr;
 
   for (;;) {
-    if (tid == 0) { sm.scan = atomicAdd(bv.work_counter, 1); sm.tlast = clock64(); }
+    // ---- claim units for the free slots ------------------------------------------------------------------------------
+    if (tid == 0) {
+      int nact = 0, nfresh = 0;
+      for (int s = 0; s < S; ++s) {
+        Smem& sm = slots[s];
+        if (sm.scan < 0 && !cta.exhausted) {
+          const int u = atomicAdd(bv.work_counter, 1);
+          if (u < bv.n_scans) { sm.scan = u; sm.fresh = 1; } else cta.exhausted = 1;
+        }
+        if (sm.scan >= 0) ++nact;
+        if (sm.fresh) ++nfresh;
+      }
+      cta.n_active = nact; cta.any_fresh = nfresh;
+    }
     __syncthreads();
-    const int scan = sm.scan;
-    if (scan >= bv.n_scans) {
+    if (cta.n_active == 0) {
       if (bv.timers && tid == 0) {  // busy time of this CTA: sum and max over CTAs give the tail imbalance
         const unsigned long long busy = (unsigned long long)(clock64() - t_cta0);
         atomicAdd((unsigned long long*)&bv.timers[26], busy);
@@ -92,190 +309,61 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lins_ieskf_kernel(const __
       }
       break;
     }
-
-    // ---- prior -> shared ---------------------------------------------------------------------------------
-    if (tid < 20) { double v = tid < 19 ? bv.state_in[(size_t)scan * 20 + tid] : 0.0; sm.prior[tid] = v; sm.lin[tid] = v; }
-    for (int e = tid; e < 324; e += kThreads) {
-      const int r = e / 18, c = e % 18;
-      sm.P[e] = bv.cov_in[(size_t)scan * 324 + c * 18 + r];
-    }
-    if (tid == 0) { sm.flags[0] = sm.flags[1] = sm.flags[2] = sm.flags[3] = 0; sm.residualNorm = 1e6; }
-    {
-      const int ts0 = bv.ts_off[scan], Ts = bv.ts_off[scan + 1] - ts0;
-      const int tc0 = bv.tc_off[scan], Tc = bv.tc_off[scan + 1] - tc0;
-      build_ring_table(bv.ts + ts0, Ts, sm.rsS, &sm.sortedS);
-      build_ring_table(bv.tc + tc0, Tc, sm.rsC, &sm.sortedC);
-      // the search index (≙ kdtree*->setInputCloud, StateEstimator.hpp:363-364 / :1158-1159), built on device:
-      // (ring, azimuth-bin) counting sort of both clouds, into shared memory when they fit
+    LINS_TICK(1);
+    if (cta.any_fresh) {
+      for (int s = 0; s < S; ++s)
+        if (slots[s].fresh) unit_prologue<MODE>(cta, slots[s], bv, kp, pb, s);
       if (tid == 0) {
-        const bool ok = sm.sortedS && sm.sortedC && bv.nn_s == nullptr && bv.nn_c == nullptr && Ts < (1 << 24) && Tc < (1 << 24);  // slot payload = ring (8 bits) | index (24 bits)
-        sm.az_ok = ok ? 1 : 0;
-        sm.nringsS = ok && Ts > 0 ? (int)bv.ts[ts0 + Ts - 1].w + 1 : 0;  // ring-sorted: the last point has the largest ring
-        sm.nringsC = ok && Tc > 0 ? (int)bv.tc[tc0 + Tc - 1].w + 1 : 0;
-        sm.nbS = az_bins_for(sm.nringsS, kAzTabS);
-        sm.nbC = az_bins_for(sm.nringsC, kAzTabC);
+        int leg = 0, idx = 0;
+        for (int s = 0; s < S; ++s) if (slots[s].scan >= 0) { if (slots[s].az_ok) idx = 1; else leg = 1; }
+        cta.any_legacy = leg; cta.any_indexed = idx;
       }
       __syncthreads();
-      pb.azS = Ts <= bv.cap_s ? az_smem : bv.az_s + ts0;
-      pb.azC = Tc <= bv.cap_c ? az_smem + bv.cap_s : bv.az_c + tc0;
-      if (sm.az_ok) {
-        az_build<kAzTabS>(bv.ts + ts0, Ts, const_cast<float4*>(pb.azS), sm.azTabS, sm.scan_tmp, sm.nbS);
-        az_build<kAzTabC>(bv.tc + tc0, Tc, const_cast<float4*>(pb.azC), sm.azTabC, sm.scan_tmp, sm.nbC);
-      }
-    }
-    lins_report* rep = bv.reports ? bv.reports + scan : nullptr;
-    int iters = 0;
-    LINS_TICK(0);
-
-    if (MODE == MODE_ASSOC || MODE == MODE_ICP_REDUCE) {
-      if (warp == 0) iter_consts_warp0(sm);
-      __syncthreads();
-      association_pass<MODE>(sm, bv, kp, scan, kp.iter0, pb, true);
-      if (bv.accum) {
-        if (tid < kNAcc) bv.accum[(size_t)scan * 32 + tid] = sm.acc[tid];
-        if (tid == 32) { bv.accum[(size_t)scan * 32 + 28] = (double)sm.cnt[0]; bv.accum[(size_t)scan * 32 + 29] = (double)sm.cnt[1]; }
-      }
-      __syncthreads();
-      continue;
+      LINS_TICK(0);
     }
 
-    // ---- the iterated update (StateEstimator.hpp:475-581) ---------------------------------------------------
-    // One block barrier separates the data-parallel part of an iteration (association_pass) from its serial tail,
-    // which warp 0 runs alone: finish the reduction, 6x6 gain system, update, convergence logic, and the constants of
-    // the NEXT iteration (so the loop has no other barrier of its own).
-    const int nq_scan = (bv.qs_off[scan + 1] - bv.qs_off[scan]) + (bv.qc_off[scan + 1] - bv.qc_off[scan]);
-    if (warp == 0) iter_consts_warp0(sm);
-    __syncthreads();
-    for (int iter = 0; iter < kp.num_iter; ++iter) {
-      const long long t_it0 = (bv.timers && tid == 0) ? clock64() : 0;
-      LINS_TICK(1);
-      association_pass<MODE>(sm, bv, kp, scan, iter, pb, iter == 0);
-      if (warp == 0) {
-        if (nq_scan > 0) finish_acc_warp0(sm);  // (an empty scan has no partial sums: the update comes from the prior alone)
-        build_A6_warp0(sm);
-        LINS_TICK(18);
-        if (lane < 6) {  // y = b6 + A6 d_c on the 6 structural rows
-          double y = sm.y6[lane];
-          for (int c = 0; c < 6; ++c) y += sm.A6[lane * 6 + c] * sm.dvec[col6(c)];
-          sm.X6[lane] = y;
-        }
-        form_M6(sm, sig2, lane, 32);
-        __syncwarp();
-        const bool ok = warp_lu_cols<6>(sm.M6, sm.X6, 1);  // z = M^-1 (b6 + A6 d_c)
-        __syncwarp();
-        LINS_TICK(19);
-        double u = 0.0;
-        if (lane < 18) {  // K (r + H d) = P[:,c] z
-          double kx = 0;
-          for (int c = 0; c < 6; ++c) kx += sm.P[lane * 18 + col6(c)] * sm.X6[c];
-          u = ok ? (-kx + sm.dvec[lane]) : __longlong_as_double(0x7ff8000000000000ll);
-        }
-        const bool hasNaN = __ballot_sync(0xffffffffu, u != u) != 0u;  // :553-558
-        if (u != u) u = 0.0;
-        if (lane < 18) sm.upd[lane] = u;
-        __syncwarp();
-        double nrm = 0.0;  // lane 0: ||update||^2 (sequential order), lane 1: ||residual||^2
-        if (lane == 0) for (int a = 0; a < 18; ++a) nrm += sm.upd[a] * sm.upd[a];
-        if (lane == 1) nrm = sm.acc[27];
-        nrm = sqrt(nrm);
-        const double un = __shfl_sync(0xffffffffu, nrm, 0), rnorm = __shfl_sync(0xffffffffu, nrm, 1);
-        LINS_TICK(21);
-        if (lane == 0) {
-          if (rep) {
-            rep->m_surf[iter] = sm.cnt[0]; rep->m_corner[iter] = sm.cnt[1];
-            rep->residual_norm[iter] = rnorm; rep->update_norm[iter] = un;
-          }
-          if (hasNaN) {  // :559-563
-            sm.flags[2] = 1; sm.flags[1] = 1; sm.flags[3] = 1;
-          } else if (rnorm > sm.residualNorm * 10) {  // :566-570
-            sm.flags[1] = 1; sm.flags[3] = 1;
-          } else {
-            box_plus(sm);  // :573
-            if (un <= 1e-2 && !kp.force_all_iters) { sm.flags[0] = 1; sm.flags[3] = 1; }  // :576-578
-            sm.residualNorm = rnorm;
-          }
+    // ---- one pass of every resident unit (StateEstimator.hpp:475-581) -----------------------------------------------
+    association_pass<MODE>(cta, slots, bv, kp, pb);
+    if (MODE == MODE_IESKF) {
+      if (warp < S && slots[warp].run) unit_tail(cta, slots[warp], bv, kp, pb, warp, sig2);
+    } else {
+      if (warp < S && slots[warp].run) {  // single-pass modes: the 28 sums + counts are the result
+        Smem& sm = slots[warp];
+        const int lane = tid & 31;
+        const int scan = sm.scan;
+        finish_acc_warp0(sm, pb.wacc + (size_t)warp * pb.nvw * kNAcc, pb.wcnt + (size_t)warp * pb.nvw * 2, (sm.ns + sm.nc + 31) >> 5);
+        if (bv.accum) {
+          if (lane < kNAcc) bv.accum[(size_t)scan * 32 + lane] = sm.acc[lane];
+          if (lane == 28) bv.accum[(size_t)scan * 32 + 28] = (double)sm.cnt[0];
+          if (lane == 29) bv.accum[(size_t)scan * 32 + 29] = (double)sm.cnt[1];
         }
         __syncwarp();
-        LINS_TICK(23);
-        if (!sm.flags[3] && iter + 1 < kp.num_iter) iter_consts_warp0(sm);
-        LINS_TICK(25);
+        if (lane == 0) { sm.scan = -1; sm.run = 0; }
       }
-      __syncthreads();
-      LINS_TICK(8);
-      if (bv.timers && tid == 0 && iter == 0) atomicAdd((unsigned long long*)&bv.timers[24], (unsigned long long)(clock64() - t_it0));
-      iters = iter + 1;
-      if (sm.flags[3]) break;
-    }
-
-    // ---- exit: covariance + outputs (StateEstimator.hpp:585-599) -------------------------------------------
-    const bool diverged = sm.flags[1] != 0;
-    if (!diverged && iters > 0) {
-      // Joseph form with the LAST iteration's K, H, R (:595-596), all through the 6x6 system:
-      //   K H = U E_c^T,  U = P[:,c] M^-1 A6 ;   K R K^T = sig2 U V^T,  V = P[:,c] M^-1
-      form_M6(sm, sig2, tid, kThreads);
-      for (int e = tid; e < 72; e += kThreads) {  // right-hand sides [A6 | I6]
-        const int a = e / 12, c = e % 12;
-        sm.X6[e] = c < 6 ? sm.A6[a * 6 + c] : (a == c - 6 ? 1.0 : 0.0);
-      }
-      __syncthreads();
-      if (warp == 0) {
-        const bool ok = warp_lu_cols<6>(sm.M6, sm.X6, 12);
-        if (!ok) for (int e = lane; e < 72; e += 32) sm.X6[e] = __longlong_as_double(0x7ff8000000000000ll);
-      }
-      __syncthreads();
-      for (int t = tid; t < 216; t += kThreads) {
-        const int which = t / 108, e = t % 108, a = e / 6, c = e % 6;
-        double sacc = 0;
-        for (int k = 0; k < 6; ++k) sacc += sm.P[a * 18 + col6(k)] * sm.X6[k * 12 + c + 6 * which];
-        (which ? sm.V : sm.U)[e] = sacc;
-      }
-      __syncthreads();
-      for (int e = tid; e < 324; e += kThreads) {  // X = (I - K H) P = P - U P[c,:]
-        const int i = e / 18, j = e % 18;
-        double sacc = sm.P[e];
-        for (int c = 0; c < 6; ++c) sacc -= sm.U[i * 6 + c] * sm.P[col6(c) * 18 + j];
-        sm.X[e] = sacc;
-      }
-      __syncthreads();
-      for (int e = tid; e < 324; e += kThreads) {  // P <- X (I - K H)^T + sig2 U V^T
-        const int i = e / 18, j = e % 18;
-        double sacc = sm.X[e], t = 0;
-        for (int c = 0; c < 6; ++c) { sacc -= sm.X[i * 18 + col6(c)] * sm.U[j * 6 + c]; t += sm.U[i * 6 + c] * sm.V[j * 6 + c]; }
-        sm.P[e] = sacc + t * sig2;
-      }
-      __syncthreads();
-    }
-    // state_out / cov_out
-    if (tid < 20) bv.state_out[(size_t)scan * 20 + tid] = diverged ? sm.prior[tid] : sm.lin[tid];
-    for (int e = tid; e < 324; e += kThreads) {
-      const int r = e / 18, c = e % 18;
-      double v;
-      if (diverged) v = bv.cov_in[(size_t)scan * 324 + c * 18 + r];
-      else if (iters > 0) v = 0.5 * (sm.P[r * 18 + c] + sm.P[c * 18 + r]);  // enforceSymmetry (:597)
-      else v = sm.P[r * 18 + c];
-      bv.cov_out[(size_t)scan * 324 + c * 18 + r] = v;
-    }
-    if (tid == 0) {
-      lins_scan_result& o = bv.results[scan];
-      o.scan_id = scan;
-      o.iters = (uint16_t)iters;
-      o.flags = (uint16_t)((sm.flags[0] ? 1 : 0) | (sm.flags[1] ? 2 : 0) | (sm.flags[2] ? 4 : 0));
-      const double* st = diverged ? sm.prior : sm.lin;
-      o.pose[0] = st[0]; o.pose[1] = st[1]; o.pose[2] = st[2];
-      o.pose[3] = st[6]; o.pose[4] = st[7]; o.pose[5] = st[8]; o.pose[6] = st[9];
-      if (rep) { rep->iters = iters; rep->converged = sm.flags[0]; rep->diverged = sm.flags[1]; rep->has_nan = sm.flags[2]; }
     }
     __syncthreads();
-    LINS_TICK(9);
+    LINS_TICK(8);
+    if (MODE == MODE_IESKF && cta.any_finished) {
+      for (int s = 0; s < S; ++s) {
+        if (!slots[s].finished) continue;  // (uniform: shared flag)
+        unit_exit(cta, slots[s], bv, sig2);
+        if (tid == 0) { slots[s].scan = -1; slots[s].finished = 0; slots[s].run = 0; }
+      }
+      if (tid == 0) cta.any_finished = 0;
+      __syncthreads();
+      LINS_TICK(9);
+    }
   }
 }
 
 
 // Split "Jacobian kernel" (SURVEY.md §8(d) unit U1; rows A5-A9 form B given the correspondence IDs).
 // One warp per scan: streams the scan's queries (16 B each, coalesced) and IDs (12 / 8 B, coalesced), gathers
-// the 3 / 2 matched targets (16 B each), recomputes de-skew, residual, weight and Jacobian row, and reduces
-// the 28 sums per scan with a fixed shuffle tree.  Nothing is staged in shared memory: with >= 4096 resident
-// scans the working set exceeds L2 and the kernel is bound by HBM traffic + f64 issue.
+// the 3 / 2 matched targets (16 B each), recomputes de-skew, residual, weight and Jacobian row.  Every trip of 32
+// queries is folded across the warp straight away (warp_fold_row: lane e owns sum e), so a lane carries ONE running
+// sum instead of 28 accumulators: few registers, many resident warps to hide the dependent ID -> target gathers; the
+// next trip's query and IDs are loaded before the current trip's arithmetic.  Nothing is staged in shared memory: with
+// >= 4096 resident scans the working set exceeds L2 and the kernel is bound by HBM traffic + f64 issue.
 template <int kJacThreads, int kJacMinBlocks>
 __global__ void __launch_bounds__(kJacThreads, kJacMinBlocks) lins_jacobian_kernel(const __grid_constant__ BatchView bv,
                                                                                 const __grid_constant__ KParams kp) {
@@ -284,7 +372,7 @@ __global__ void __launch_bounds__(kJacThreads, kJacMinBlocks) lins_jacobian_kern
   for (int scan = (blockIdx.x * kJacThreads + threadIdx.x) >> 5; scan < bv.n_scans; scan += warps_per_grid) {
     // per-scan constants (every lane computes the same values)
     const double* st = bv.state_in + (size_t)scan * 20;
-    double rn[3] = {st[0], st[1], st[2]};
+    const double rn0 = st[0], rn1 = st[1], rn2 = st[2];
     q4 q; q.x = st[6]; q.y = st[7]; q.z = st[8]; q.w = st[9];
     const d3 phi = Quat2axis(q);
     const m3 R = qtoR(q);
@@ -293,47 +381,56 @@ __global__ void __launch_bounds__(kJacThreads, kJacMinBlocks) lins_jacobian_kern
     const float4* __restrict__ tgtS = bv.ts + bv.ts_off[scan];
     const float4* __restrict__ tgtC = bv.tc + bv.tc_off[scan];
     const int Ts = bv.ts_off[scan + 1] - bv.ts_off[scan], Tc = bv.tc_off[scan + 1] - bv.tc_off[scan];
-    double acc[kNAcc];
-#pragma unroll
-    for (int k = 0; k < kNAcc; ++k) acc[k] = 0.0;
-    int cs = 0, cc = 0;
     const bool weighted = kp.iter0 >= kp.icp_freq;
-    for (int i = lane; i < ns + nc; i += 32) {
-      const bool surf = i < ns;
-      const float4 p = surf ? __ldg(bv.qs + qs0 + i) : __ldg(bv.qc + qc0 + (i - ns));
-      // A2 de-skew
-      float fi = p.w - (float)((int)p.w);
-      double s = (1.f / kp.scan_period) * fi;
-      q4 rq = axis2Quat(mk3(s * phi.x, s * phi.y, s * phi.z));
-      d3 rp = qrot(rq, mk3(p.x, p.y, p.z));
-      float4 sel;
-      sel.x = (float)(rp.x + s * rn[0]); sel.y = (float)(rp.y + s * rn[1]); sel.z = (float)(rp.z + s * rn[2]); sel.w = p.w;
-      float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-      bool ok = false;
-      if (surf) {
+    double total = 0.0;  // lane e: running sum of entry e
+    int cs = 0, cc = 0;
+    auto fetch = [&](int i, float4& p, int& i1, int& i2, int& i3) {
+      p = make_float4(0.f, 0.f, 0.f, 0.f); i1 = -1; i2 = -1; i3 = -1;
+      if (i < ns) {
+        p = __ldg(bv.qs + qs0 + i);
         const int* id = bv.ind_s + 3 * (size_t)(qs0 + i);
-        const int i1 = __ldg(id), i2 = __ldg(id + 1), i3 = __ldg(id + 2);
-        if (i2 >= 0 && i3 >= 0 && i1 >= 0 && i1 < Ts && i2 < Ts && i3 < Ts)
-          ok = plane_residual(sel, __ldg(&tgtS[i1]), __ldg(&tgtS[i2]), __ldg(&tgtS[i3]), weighted, coeff);
-      } else {
+        i1 = __ldg(id); i2 = __ldg(id + 1); i3 = __ldg(id + 2);
+      } else if (i < ns + nc) {
+        p = __ldg(bv.qc + qc0 + (i - ns));
         const int* id = bv.ind_c + 2 * (size_t)(qc0 + (i - ns));
-        const int i1 = __ldg(id), i2 = __ldg(id + 1);
-        if (i2 >= 0 && i1 >= 0 && i1 < Tc && i2 < Tc) ok = line_residual(sel, __ldg(&tgtC[i1]), __ldg(&tgtC[i2]), weighted, coeff);
+        i1 = __ldg(id); i2 = __ldg(id + 1);
       }
-      if (ok) {
-        accumulate_row(p, coeff, R.m, kp.lidar_scale, acc);
-        if (surf) ++cs; else ++cc;
+    };
+    float4 pn; int n1, n2, n3;
+    fetch(lane, pn, n1, n2, n3);
+    for (int i0 = 0; i0 < ns + nc; i0 += 32) {
+      const int i = i0 + lane;
+      const float4 p = pn;
+      const int i1 = n1, i2 = n2, i3 = n3;
+      const bool surf = i < ns;
+      // gathers of this trip, then the next trip's streaming loads: both in flight during the arithmetic below
+      float4 t1 = make_float4(0.f, 0.f, 0.f, 0.f), t2 = t1, t3 = t1;
+      bool have = false;
+      if (surf) {
+        if (i2 >= 0 && i3 >= 0 && i1 >= 0 && i1 < Ts && i2 < Ts && i3 < Ts) { t1 = __ldg(&tgtS[i1]); t2 = __ldg(&tgtS[i2]); t3 = __ldg(&tgtS[i3]); have = true; }
+      } else if (i < ns + nc) {
+        if (i2 >= 0 && i1 >= 0 && i1 < Tc && i2 < Tc) { t1 = __ldg(&tgtC[i1]); t2 = __ldg(&tgtC[i2]); have = true; }
       }
+      fetch(i + 32, pn, n1, n2, n3);
+      double g[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, r = 0.0;
+      bool ok = false;
+      if (have) {
+        // A2 de-skew
+        const float fi = p.w - (float)((int)p.w);
+        const double s = (1.f / kp.scan_period) * fi;
+        const q4 rq = axis2Quat(mk3(s * phi.x, s * phi.y, s * phi.z));
+        const d3 rp = qrot(rq, mk3(p.x, p.y, p.z));
+        float4 sel;
+        sel.x = (float)(rp.x + s * rn0); sel.y = (float)(rp.y + s * rn1); sel.z = (float)(rp.z + s * rn2); sel.w = p.w;
+        float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+        ok = surf ? plane_residual(sel, t1, t2, t3, weighted, coeff) : line_residual(sel, t1, t2, weighted, coeff);
+        if (ok) jacobian_row(p, coeff, R.m, kp.lidar_scale, g, r);
+      }
+      total += warp_fold_row(g, r);
+      cs += __popc(__ballot_sync(0xffffffffu, ok && surf));
+      cc += __popc(__ballot_sync(0xffffffffu, ok && !surf));
     }
-#pragma unroll
-    for (int k = 0; k < kNAcc; ++k) {
-      double v = acc[k];
-#pragma unroll
-      for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-      if (lane == (k & 31)) bv.accum[(size_t)scan * 32 + k] = v;
-    }
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) { cs += __shfl_xor_sync(0xffffffffu, cs, m); cc += __shfl_xor_sync(0xffffffffu, cc, m); }
+    if (lane < kNAcc) bv.accum[(size_t)scan * 32 + lane] = total;
     if (lane == 28) bv.accum[(size_t)scan * 32 + 28] = (double)cs;
     if (lane == 29) bv.accum[(size_t)scan * 32 + 29] = (double)cc;
   }
@@ -403,6 +500,7 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   size_t nqs = 0, nqc = 0, nts = 0, ntc = 0;
   int max_q = 0;
   DevBuf<float4> qs, qc, ts, tc, az_s, az_c;
+  DevBuf<unsigned char> qscratch;  // per-CTA per-query arrays of units too large for shared memory
   int max_ts = 0, max_tc = 0;
   DevBuf<int> qs_off, qc_off, ts_off, tc_off, ind_s, ind_c, counter;
   DevBuf<long long> timers;
@@ -417,7 +515,7 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   PinBuf<lins_scan_result> h_results;
   PinBuf<lins_report> h_reports;
   void release() {
-    qs.release(); qc.release(); ts.release(); tc.release(); az_s.release(); az_c.release(); qs_off.release(); qc_off.release(); ts_off.release();
+    qs.release(); qc.release(); ts.release(); tc.release(); az_s.release(); az_c.release(); qscratch.release(); qs_off.release(); qc_off.release(); ts_off.release();
     tc_off.release(); ind_s.release(); ind_c.release(); counter.release(); state_in.release(); cov_in.release();
     state_out.release(); cov_out.release(); accum.release(); results.release(); reports.release(); sel_s.release();
     sel_c.release(); coeff_s.release(); coeff_c.release(); mask_s.release(); mask_c.release(); h_pts.release();
@@ -447,7 +545,7 @@ struct lins_ctx {
   bool tree_is_map = true;
   bool timers_on = false;
   bool verbose = false;  // LINS_VERBOSE: print the launch configuration
-  int force_cap_s = -1, force_cap_c = -1;  // tuning knobs (LINS_CAP_S / LINS_CAP_C): upper limits of the shared-memory copies
+  int force_slots = 0;  // tuning knob (LINS_SLOTS): resident units per CTA
   DevBuf<float4> tmp_pts;
   DevBuf<double> tmp_lin;
   PinBuf<float4> h_tmp;
@@ -520,24 +618,38 @@ int validate_params(const lins_params* p) {
 }
 
 template <int MODE>
-int launch_mode(lins_ctx* ctx, const BatchView& bv_in, const KParams& kp) {
+int launch_mode(lins_ctx* ctx, Resident& r, const BatchView& bv_in, const KParams& kp) {
   BatchView bv = bv_in;
-  // keep the sorted target copies in shared memory when they fit; the corner copy is small and goes first
-  if (ctx->force_cap_s >= 0) bv.cap_s = std::min(bv.cap_s, ctx->force_cap_s);
-  if (ctx->force_cap_c >= 0) bv.cap_c = std::min(bv.cap_c, ctx->force_cap_c);
-  if ((int)smem_bytes_for(bv.qtile, bv.cap_s, bv.cap_c) > ctx->max_smem_optin) {
-    if ((int)smem_bytes_for(bv.qtile, 0, bv.cap_c) <= ctx->max_smem_optin) bv.cap_s = 0;
-    else { bv.cap_s = 0; bv.cap_c = 0; }
+  // resident units per CTA: as many as fit shared memory (per-query arrays of every slot + fixed part), but no more
+  // than the batch can fill on every SM
+  const int limit = ctx->max_smem_optin;
+  int want = std::min(kMaxSlots, std::max(1, (bv.n_scans + ctx->sm_count - 1) / ctx->sm_count));
+  if (ctx->force_slots > 0) want = std::min(kMaxSlots, ctx->force_slots);
+  int S = 0;
+  for (int s = want; s >= 1; --s)
+    if ((int)(smem_fixed_bytes(s, bv.qtile) + query_array_bytes(s, bv.qtile)) <= limit) { S = s; break; }
+  size_t smem;
+  bv.qscratch = nullptr; bv.qscratch_stride = 0;
+  if (S == 0) {  // even one unit's per-query arrays exceed shared memory: keep them in a per-CTA global scratch
+    S = 1;
+    smem = smem_fixed_bytes(1, bv.qtile);
+    if ((int)smem > limit) return fail(ctx, LINS_E_TOOBIG, "unit too large for the fused kernel");
+    bv.qscratch_stride = query_array_bytes(1, bv.qtile);
+  } else {
+    smem = smem_fixed_bytes(S, bv.qtile) + query_array_bytes(S, bv.qtile);
   }
-  size_t smem = smem_bytes_for(bv.qtile, bv.cap_s, bv.cap_c);
-  if ((int)smem > ctx->max_smem_optin) return fail(ctx, LINS_E_TOOBIG, "query tile does not fit shared memory");
+  bv.nslots = S;
   CK(cudaFuncSetAttribute(lins_ieskf_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lins_ieskf_kernel<MODE>, kThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  int grid = std::min(bv.n_scans, ctx->sm_count * per_sm);
+  int grid = std::min((bv.n_scans + S - 1) / S, ctx->sm_count * per_sm);
   if (grid < 1) grid = 1;
-  if (ctx->verbose) std::fprintf(stderr, "[lins_gpu] mode %d: %d threads, %zu B shared, %d CTA/SM, grid %d, cap_s %d cap_c %d qtile %d\n", MODE, kThreads, smem, per_sm, grid, bv.cap_s, bv.cap_c, bv.qtile);
+  if (bv.qscratch_stride) {
+    CK(r.qscratch.reserve(bv.qscratch_stride * (size_t)grid));
+    bv.qscratch = r.qscratch.p;
+  }
+  if (ctx->verbose) std::fprintf(stderr, "[lins_gpu] mode %d: %d threads, %zu B shared, %d CTA/SM, grid %d, slots %d qtile %d%s\n", MODE, kThreads, smem, per_sm, grid, S, bv.qtile, bv.qscratch ? " (per-query arrays in global scratch)" : "");
   CK(cudaMemsetAsync(bv.work_counter, 0, sizeof(int), ctx->stream));
   lins_ieskf_kernel<MODE><<<grid, kThreads, smem, ctx->stream>>>(bv, kp);
   CK(cudaGetLastError());
@@ -545,11 +657,11 @@ int launch_mode(lins_ctx* ctx, const BatchView& bv_in, const KParams& kp) {
   return LINS_OK;
 }
 
-int launch(lins_ctx* ctx, const BatchView& bv, const KParams& kp) {
+int launch(lins_ctx* ctx, Resident& r, const BatchView& bv, const KParams& kp) {
   switch (kp.mode) {
-    case MODE_IESKF: return launch_mode<MODE_IESKF>(ctx, bv, kp);
-    case MODE_ASSOC: return launch_mode<MODE_ASSOC>(ctx, bv, kp);
-    case MODE_ICP_REDUCE: return launch_mode<MODE_ICP_REDUCE>(ctx, bv, kp);
+    case MODE_IESKF: return launch_mode<MODE_IESKF>(ctx, r, bv, kp);
+    case MODE_ASSOC: return launch_mode<MODE_ASSOC>(ctx, r, bv, kp);
+    case MODE_ICP_REDUCE: return launch_mode<MODE_ICP_REDUCE>(ctx, r, bv, kp);
   }
   return fail(ctx, LINS_E_INVALID, "bad kernel mode");
 }
@@ -557,7 +669,6 @@ int launch(lins_ctx* ctx, const BatchView& bv, const KParams& kp) {
 int choose_qtile(int max_q) {
   int q = ((max_q + 31) / 32) * 32;
   if (q < 32) q = 32;
-  if (q > 1024) q = 1024;
   return q;
 }
 
@@ -591,7 +702,6 @@ BatchView view_of(const Resident& r, bool reports, bool trace) {
   bv.results = r.results.p; bv.reports = reports ? r.reports.p : nullptr;
   bv.ind_s = r.ind_s.p; bv.ind_c = r.ind_c.p;
   bv.az_s = r.az_s.p; bv.az_c = r.az_c.p;
-  bv.cap_s = r.max_ts; bv.cap_c = r.max_tc;  // launch_mode() zeroes what does not fit shared memory
   if (trace) {
     bv.sel_s = r.sel_s.p; bv.sel_c = r.sel_c.p; bv.coeff_s = r.coeff_s.p; bv.coeff_c = r.coeff_c.p;
     bv.mask_s = r.mask_s.p; bv.mask_c = r.mask_c.p;
@@ -677,8 +787,7 @@ int lins_gpu_create(const lins_params* params, int device, void* stream, lins_ct
   ctx->sm_count = prop.multiProcessorCount;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   ctx->verbose = std::getenv("LINS_VERBOSE") != nullptr;
-  if (const char* e = std::getenv("LINS_CAP_S")) ctx->force_cap_s = std::atoi(e);
-  if (const char* e = std::getenv("LINS_CAP_C")) ctx->force_cap_c = std::atoi(e);
+  if (const char* e = std::getenv("LINS_SLOTS")) ctx->force_slots = std::atoi(e);
   if (stream) { ctx->stream = (cudaStream_t)stream; ctx->own_stream = false; }
   else {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return LINS_E_CUDA; }
@@ -734,7 +843,7 @@ int lins_gpu_ieskf(lins_ctx* ctx, const lins_point* surf_flat, int ns, const lin
   Resident& r = ctx->single;
   BatchView bv = single_view(ctx, false);
   CK(cudaMemsetAsync(r.reports.p, 0, sizeof(lins_report), ctx->stream));
-  rc = launch(ctx, bv, make_kparams(ctx->prm, MODE_IESKF, 0));
+  rc = launch(ctx, r, bv, make_kparams(ctx->prm, MODE_IESKF, 0));
   if (rc != LINS_OK) return rc;
   CK(r.h_state_out.reserve(20)); CK(r.h_cov_out.reserve(324)); CK(r.h_reports.reserve(1));
   CK(cudaMemcpyAsync(r.h_state_out.p, r.state_out.p, sizeof(double) * 20, cudaMemcpyDeviceToHost, ctx->stream));
@@ -758,7 +867,7 @@ int lins_gpu_associate(lins_ctx* ctx, const lins_point* surf_flat, int ns, const
   if (rc != LINS_OK) return rc;
   Resident& r = ctx->single;
   BatchView bv = single_view(ctx, true);
-  rc = launch(ctx, bv, make_kparams(ctx->prm, MODE_ASSOC, iter));
+  rc = launch(ctx, r, bv, make_kparams(ctx->prm, MODE_ASSOC, iter));
   if (rc != LINS_OK) return rc;
   auto d2h = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
     if (!dst || bytes == 0) return cudaSuccess;
@@ -870,7 +979,7 @@ int lins_gpu_batch_run(lins_ctx* ctx) {
     CK(cudaMemsetAsync(r.timers.p, 0, sizeof(long long) * 64, ctx->stream));
     bv.timers = r.timers.p;
   }
-  return launch(ctx, bv, make_kparams(ctx->prm, MODE_IESKF, 0));
+  return launch(ctx, r, bv, make_kparams(ctx->prm, MODE_IESKF, 0));
 }
 
 int lins_gpu_batch_download(lins_ctx* ctx, double* state_out, double* cov_out, lins_scan_result* results,
@@ -1141,12 +1250,13 @@ int lins_gpu_estimate_transform(lins_ctx* ctx, const lins_point* surf_flat, int 
     int rc = stage_single(ctx, surf_flat, ns, corner_sharp, nc, lin, nullptr, false);
     if (rc != LINS_OK) return rc;
     BatchView bv = single_view(ctx, false);
-    rc = launch(ctx, bv, make_kparams(ctx->prm, MODE_ICP_REDUCE, iter));
+    rc = launch(ctx, r, bv, make_kparams(ctx->prm, MODE_ICP_REDUCE, iter));
     if (rc != LINS_OK) return rc;
     CK(r.h_accum.reserve(32));
     CK(cudaMemcpyAsync(r.h_accum.p, r.accum.p, sizeof(double) * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const double* a = r.h_accum.p;
+    if (ctx->verbose) { std::fprintf(stderr, "[lins_gpu] icp iter %d:", iter); for (int k = 0; k < 30; ++k) std::fprintf(stderr, " %.6g", a[k]); std::fprintf(stderr, "\n"); }
     if (a[28] < 10) continue;  // "Insufficient matched surfs..." (:1175-1178)
     if (a[29] < 5) continue;   // "Insufficient matched corners..." (:1181-1184)
     linalg::Mat<6> JTJ;

@@ -1,7 +1,8 @@
-// Fused iterated-ESKF update kernel for sm_100a (B200).
+// Fused iterated-ESKF update kernel for sm_100a (B200): device functions shared by its phases.
 //
-// One CTA owns one scan (a "unit": query features of the new scan, target features of the last scan, prior)
-// and runs the WHOLE performIESKF loop (reference lins/include/StateEstimator.hpp:465-600) on device:
+// A CTA keeps up to kMaxSlots units resident ("slots"; a unit = query features of the new scan, target features of
+// the last scan, prior) and runs the WHOLE performIESKF loop (reference lins/include/StateEstimator.hpp:465-600) for
+// all of them in lockstep, phase by phase:
 //   A2  transformToStart de-skew of every query               (:1066-1080)   f64 math, f32 store
 //   A3/4 exact 1-NN + the +-2.5-ring index walks               (:844-915, :970-1029) f32, bit-exact indices
 //   A5/6 point-to-plane / point-to-line residual + coeff       (:917-951, :1031-1060)
@@ -9,11 +10,13 @@
 //        (21 + 6 + 1 scalars per scan; SURVEY.md §8 A9 form B) — H (Mx18) and S (MxM) are never formed
 //   A10 boxMinus / gain solve / NaN + divergence tests / boxPlus / convergence (:548-580)
 //   A11 Joseph covariance update at exit                        (:595-598)
-// CTAs pull scans from a global counter (persistent grid sized to the SM count), so iteration-count imbalance
-// between scans does not idle SMs.  Queries + prior are staged into shared memory with 1-D TMA
-// (cp.async.bulk + mbarrier); the target clouds stay in global memory as packed float4 (x,y,z,intensity)
-// and are read through L1/L2 with broadcast or coalesced 16-B loads.  All reductions use a fixed shuffle tree
-// + fixed-order cross-warp sum, so results are run-to-run deterministic (no floating-point atomics).
+// Why lockstep slots: the kernel's per-iteration code is ~100 KB of straight-line f64 / search code, far beyond the
+// 32 KB instruction cache of an SM; a lone warp (the serial tail of an iteration, a late search) runs at the speed
+// of instruction fetch from L2.  With several units per CTA every fetched instruction serves all of them: the
+// thread-per-query phases cover the queries of every slot, the warp-per-search phases pull from one work list, and
+// the serial tails of the slots run side by side on different warps.  CTAs pull units from a global counter as
+// slots fall free, so iteration-count imbalance between units does not idle SMs.  All reductions use a fixed
+// shuffle tree + fixed-order sums, so results are run-to-run deterministic (no floating-point atomics).
 #pragma once
 #include "../../../include/lins_gpu.h"
 #include "lins_device_math.cuh"
@@ -29,8 +32,9 @@ namespace lins_dev {
 constexpr int kThreads = LINS_THREADS;   // threads per CTA (one unit per CTA); LINS_MIN_CTAS = resident CTAs per SM the register budget is set for
 constexpr int kMinCtas = LINS_MIN_CTAS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kRingTab = 260;   // ring-start table: first target index with ring >= r, r = 0..259
-constexpr int kMaxRing = 256;   // rings outside [0, kMaxRing) or unsorted clouds take the sequential walk
+constexpr int kMaxSlots = 4;    // resident units per CTA (<= kWarps: warp w runs the serial tail of slot w)
+constexpr int kMaxRing = 128;   // rings outside [0, kMaxRing) or unsorted clouds take the brute-force search + sequential walk
+                                // ((ring << 24 | index) must stay non-negative: -1 is the "no closest point" sentinel)
 constexpr int kNAcc = 28;       // 21 (sym 6x6) + 6 (g*r) + 1 (r*r)
 constexpr int kNNChunk = 1024;  // targets per brute-force work item
 constexpr int kAzTabS = 4096;   // (ring, azimuth bin) table entries, surf targets (see lins_assoc_az.cuh)
@@ -62,12 +66,14 @@ struct BatchView {
   float* coeff_s; float* coeff_c;        // optional (4 per query)
   unsigned char* mask_s; unsigned char* mask_c;  // optional
   double* accum;                         // n x 32 : 28 accumulators + m_surf + m_corner (modes 2,3)
-  float4* az_s; float4* az_c;            // global scratch for the (ring, azimuth)-sorted copies when they do not fit
-                                         // shared memory; same per-scan offsets as ts / tc
-  int cap_s, cap_c;                      // points of the sorted copies held in shared memory (0 = use the scratch)
+  float4* az_s; float4* az_c;            // the (ring, azimuth)-sorted target copies built by the kernel (≙ the kd-trees),
+                                         // same per-scan offsets as ts / tc; served from L1 / L2
   int* work_counter;
-  long long* timers;                     // optional: per-phase SM cycles summed over CTAs (diagnostics), 32 slots
-  int qtile;                             // queries staged per pass
+  long long* timers;                     // optional: per-phase SM cycles summed over CTAs (diagnostics), 64 slots
+  int qtile;                             // per-slot capacity of the per-query arrays (>= the largest unit, multiple of 32)
+  int nslots;                            // resident units per CTA
+  unsigned char* qscratch;               // per-CTA global scratch for the per-query arrays when they do not fit shared
+  size_t qscratch_stride;                // memory (null: they live in shared memory)
 };
 
 struct KParams {
@@ -91,10 +97,13 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 }
 
 // shared-memory carve-up ---------------------------------------------------------------------------------
-struct Smem {
+typedef unsigned short aztab_t;  // bucket tables hold slots of the sorted copies: the indexed path needs T < 65536
+
+// one resident unit ("slot")
+struct alignas(16) Smem {
   // iteration-invariant
   double prior[20];
-  double P[324];        // prior covariance, row-major
+  double Pc[18 * 6];    // P[:, c], c = {0,1,2,6,7,8}: the only part of the prior covariance an iteration reads
   // iterate
   double lin[20];
   double phi[3];        // Quat2axis(lin q)
@@ -102,30 +111,40 @@ struct Smem {
   double Rinv[9];       // Rinvleft(-phi)
   double dvec[18];      // filterState (-) linState
   double acc[kNAcc + 4];
-  double wacc[kWarps][kNAcc];
-  int wcnt[kWarps][2];
-  int cnt[2];
   double A6[36];
   double y6[6];
   double M6[36];        // A6 P_cc + sig2 I  (6x6 gain system, see form_M6)
-  double X6[6 * 12];    // right-hand sides / solutions of the 6x6 system
-  double U[18 * 6];     // P[:,c] M^-1 A6
-  double V[18 * 6];     // P[:,c] M^-1
-  double X[18 * 18];    // (I - K H) P
+  double X6[6];         // right-hand side / solution of the gain system
   double upd[18];
   double residualNorm;
   int flags[4];         // 0 converged 1 diverged 2 has_nan 3 stop
-  int scan;
+  int cnt[2];
+  // bookkeeping
+  int scan;             // unit id, -1 = the slot is free
+  int iter;             // index of the iteration being run (iterations completed so far)
+  int fresh;            // just claimed: needs its prologue
+  int run;              // takes part in the passes
+  int finished;         // leaves after this pass (exit covariance + outputs)
+  int first_pass;       // no previous answers to seed / certify from
+  int pos_valid, pos_is_slot;  // pos[] holds this unit's correspondences; as slots of the sorted copies or original indices
+  int qs0, ns, qc0, nc, ts0, Ts, tc0, Tc;
   int sortedS, sortedC;
-  int rsS[kRingTab];
-  int rsC[kRingTab];
-  int azTabS[kAzTabS + 1];  // (ring, azimuth bin) -> first slot of the sorted surf copy
-  int azTabC[kAzTabC + 1];
-  int scan_tmp[kThreads];
-  int dbg[2];               // diagnostics (only touched when phase timers are enabled)
-  int wl_n[2], wl_head[2];  // work lists of the closest-point / walk phases (entries, next entry to hand out)
-  int az_ok;                // 1: both clouds ring-sorted + indexed (fast path); 0: legacy brute-force / plain walks
+  int az_ok;            // 1: both clouds ring-sorted + indexed (fast path); 0: brute-force 1-NN + sequential walks
   int nbS, nbC, nringsS, nringsC;
+  aztab_t azTabS[kAzTabS + 2];  // (ring, azimuth bin) -> first slot of the sorted surf copy
+  aztab_t azTabC[kAzTabC + 2];
+};
+
+// per-CTA scratch
+struct CtaMem {
+  union {
+    int build_tab[kAzTabS + 1];  // counting-sort counters / cursors while a unit's index is built
+    struct { double P[324], X[324], U[108], V[108], X6[72]; } ex;  // exit covariance of one finished unit
+  } u;
+  int scan_tmp[kThreads];
+  int wl_n[2], wl_head[2];  // work lists of the closest-point / walk phases (entries, next entry to hand out)
+  int dbg[2];               // diagnostics (only touched when phase timers are enabled)
+  int n_active, any_fresh, any_finished, any_legacy, any_indexed, exhausted;
   unsigned long long mbar;
   unsigned int phase;
   long long tlast;
@@ -136,19 +155,8 @@ struct Smem {
   do {                                                                                 \
     if (bv.timers && threadIdx.x == 0) {                                               \
       const long long _t = clock64();                                                  \
-      atomicAdd((unsigned long long*)&bv.timers[k], (unsigned long long)(_t - sm.tlast)); \
-      sm.tlast = _t;                                                                   \
-    }                                                                                  \
-  } while (0)
-
-// same, and the interval is also added to slot kf when `first` holds (first pass of a scan)
-#define LINS_TICK_F(k, kf, first)                                                       \
-  do {                                                                                 \
-    if (bv.timers && threadIdx.x == 0) {                                               \
-      const long long _t = clock64();                                                  \
-      atomicAdd((unsigned long long*)&bv.timers[k], (unsigned long long)(_t - sm.tlast)); \
-      if (first) atomicAdd((unsigned long long*)&bv.timers[kf], (unsigned long long)(_t - sm.tlast)); \
-      sm.tlast = _t;                                                                   \
+      atomicAdd((unsigned long long*)&bv.timers[k], (unsigned long long)(_t - cta.tlast)); \
+      cta.tlast = _t;                                                                   \
     }                                                                                  \
   } while (0)
 
@@ -167,18 +175,15 @@ __device__ __forceinline__ float4 transform_to_start(const float4 p, const Smem&
   return o;
 }
 
-// ring-start table: rs[r] = first index with ring >= r (valid only if the cloud is ring-sorted, rings in
-// [0, kMaxRing)).  sorted flag cleared otherwise.
-__device__ void build_ring_table(const float4* __restrict__ tgt, int T, int* rs, int* sorted_flag) {
-  for (int r = threadIdx.x; r < kRingTab; r += kThreads) rs[r] = T;
+// Is the cloud ring-sorted with every ring in [0, kMaxRing)?  (what the reference's extractFeatures emits, :727-826; the
+// (ring, azimuth) index requires it).  Block-wide; *sorted_flag is valid after the trailing barrier.
+__device__ void check_ring_sorted(const float4* __restrict__ tgt, int T, int* sorted_flag) {
   if (threadIdx.x == 0) *sorted_flag = 1;
   __syncthreads();
   for (int j = threadIdx.x; j < T; j += kThreads) {
-    int rj = (int)__ldg(&tgt[j]).w;
-    int rp = j > 0 ? (int)__ldg(&tgt[j - 1]).w : -1;
-    if (rj < 0 || rj >= kMaxRing || (j > 0 && rj < rp)) { *sorted_flag = 0; continue; }
-    if (j == 0) { for (int r = 0; r <= rj; ++r) rs[r] = 0; }
-    else if (rj != rp) { for (int r = (rp < 0 ? 0 : rp + 1); r <= rj; ++r) rs[r] = j; }
+    const int rj = (int)__ldg(&tgt[j]).w;
+    const int rp = j > 0 ? (int)__ldg(&tgt[j - 1]).w : -1;
+    if (rj < 0 || rj >= kMaxRing || (j > 0 && rj < rp)) *sorted_flag = 0;
   }
   __syncthreads();
 }
@@ -212,52 +217,6 @@ __device__ void nn_brute(const float4* sel, unsigned long long* key, int nq, con
 __device__ __forceinline__ unsigned int order_fwd(int j) { return (unsigned)j; }
 __device__ __forceinline__ unsigned int order_bwd(int j) { return 0x80000000u | (unsigned)(0x7fffffff - j); }
 __device__ __forceinline__ int order_decode(unsigned int o) { return (o & 0x80000000u) ? (0x7fffffff - (int)(o & 0x7fffffffu)) : (int)o; }
-
-// Ring walks of one query by one warp, ring-sorted fast path (StateEstimator.hpp:859-910 / :983-1024).
-template <bool SURF>
-__device__ __forceinline__ void walk_warp(const float4 s, int c, const float4* __restrict__ tgt, int T, const int* rs,
-                                          int fwdBound, float nearf, int& i2, int& i3) {
-  const int lane = threadIdx.x & 31;
-  const int cr = (int)__ldg(&tgt[c]).w;
-  const int rlo = cr - 2, rhi = cr + 3;
-  const int lo = rlo <= 0 ? 0 : (rlo >= kRingTab ? T : rs[rlo]);
-  int hi = rhi >= kRingTab ? T : (rhi <= 0 ? 0 : rs[rhi]);
-  hi = min(hi, fwdBound);
-  const unsigned long long init = pack_key(nearf, 0u);
-  unsigned long long k2 = init, k3 = init;
-  for (int j = c + 1 + lane; j < hi; j += 32) {  // forward
-    const float4 t = __ldg(&tgt[j]);
-    const float d = sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z);
-    const int rj = (int)t.w;
-    const unsigned long long k = pack_key(d, order_fwd(j));
-    if (SURF) {
-      if (rj <= cr) { if (d < nearf && k < k2) k2 = k; }
-      else { if (d < nearf && k < k3) k3 = k; }
-    } else {
-      if (rj > cr) { if (d < nearf && k < k2) k2 = k; }
-    }
-  }
-  for (int j = lo + lane; j < c; j += 32) {  // backward
-    const float4 t = __ldg(&tgt[j]);
-    const float d = sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z);
-    const int rj = (int)t.w;
-    const unsigned long long k = pack_key(d, order_bwd(j));
-    if (SURF) {
-      if (rj >= cr) { if (d < nearf && k < k2) k2 = k; }
-      else { if (d < nearf && k < k3) k3 = k; }
-    } else {
-      if (rj < cr) { if (d < nearf && k < k2) k2 = k; }
-    }
-  }
-  k2 = warp_min_u64(k2);
-  i2 = k2 == init ? -1 : order_decode((unsigned)(k2 & 0xffffffffu));
-  if (SURF) {
-    k3 = warp_min_u64(k3);
-    i3 = k3 == init ? -1 : order_decode((unsigned)(k3 & 0xffffffffu));
-  } else {
-    i3 = -1;
-  }
-}
 
 // Sequential walk, literal restatement (any ring order / values).  One thread.
 template <bool SURF>
@@ -336,82 +295,65 @@ __device__ __forceinline__ bool line_residual(const float4 sel, const float4 t1,
   return false;
 }
 
-// A7-A9: fold one accepted measurement into the per-thread accumulators.
-// g = [c ; P2 x (R^T c)]  (the Jacobian row is h = [c ; Rinv^T g_att], applied once per scan at solve time)
-__device__ __forceinline__ void accumulate_row(const float4 kp, const float4 coeff, const double* R, double lidar_scale,
-                                               double* acc) {
+// A7-A9: the factored Jacobian row of one accepted measurement.
+// g = [c ; P2 x (R^T c)]  (the Jacobian row is h = [c ; Rinv^T g_att], applied once per scan at solve time), r = residual
+__device__ __forceinline__ void jacobian_row(const float4 kp, const float4 coeff, const double* R, double lidar_scale,
+                                             double* g, double& r) {
   const double cx = coeff.x, cy = coeff.y, cz = coeff.z;
-  const double r = lidar_scale * (double)coeff.w;
+  r = lidar_scale * (double)coeff.w;
   const double ux = R[0] * cx + R[3] * cy + R[6] * cz;
   const double uy = R[1] * cx + R[4] * cy + R[7] * cz;
   const double uz = R[2] * cx + R[5] * cy + R[8] * cz;
   const double px = kp.x, py = kp.y, pz = kp.z;
-  double g[6];
   g[0] = cx; g[1] = cy; g[2] = cz;
   g[3] = py * uz - pz * uy; g[4] = pz * ux - px * uz; g[5] = px * uy - py * ux;
-  int k = 0;
-#pragma unroll
-  for (int a = 0; a < 6; ++a)
-#pragma unroll
-    for (int b = a; b < 6; ++b) acc[k++] += g[a] * g[b];
-#pragma unroll
-  for (int a = 0; a < 6; ++a) acc[21 + a] += g[a] * r;
-  acc[27] += r * r;
 }
 // ICP fallback variant (StateEstimator.hpp:1228-1258): interpolated rotation per point, rotation block first.
-__device__ __forceinline__ void accumulate_row_icp(const float4 kp, const float4 coeff, const Smem& sm, double scan_period,
-                                                   double* acc) {
+__device__ __forceinline__ void jacobian_row_icp(const float4 kp, const float4 coeff, const double* phi, double scan_period,
+                                                 double* g, double& b) {
   float fi = kp.w - (float)((int)kp.w);
   double s = (1.f / scan_period) * fi;
-  q4 rq = axis2Quat(mk3(s * sm.phi[0], s * sm.phi[1], s * sm.phi[2]));
+  q4 rq = axis2Quat(mk3(s * phi[0], s * phi[1], s * phi[2]));
   m3 R = qtoR(rq);
   const double cx = coeff.x, cy = coeff.y, cz = coeff.z;
-  const double b = -0.05 * (double)coeff.w;
+  b = -0.05 * (double)coeff.w;
   const double ux = R.m[0] * cx + R.m[3] * cy + R.m[6] * cz;
   const double uy = R.m[1] * cx + R.m[4] * cy + R.m[7] * cz;
   const double uz = R.m[2] * cx + R.m[5] * cy + R.m[8] * cz;
   const double px = kp.x, py = kp.y, pz = kp.z;
-  double g[6];
   g[0] = py * uz - pz * uy; g[1] = pz * ux - px * uz; g[2] = px * uy - py * ux;
   g[3] = cx; g[4] = cy; g[5] = cz;
-  int k = 0;
-#pragma unroll
-  for (int a = 0; a < 6; ++a)
-#pragma unroll
-    for (int c = a; c < 6; ++c) acc[k++] += g[a] * g[c];
-#pragma unroll
-  for (int a = 0; a < 6; ++a) acc[21 + a] += g[a] * b;
-  acc[27] += b * b;
 }
 
-// fixed-tree block reduction of the per-thread accumulators into sm.acc / sm.cnt
-// finish = false: stop after the per-warp partial sums are in shared memory (one barrier); the caller's warp 0
-// adds them with finish_acc_warp0.
-__device__ void block_reduce_acc(Smem& sm, double* acc, int cs, int cc, bool finish = true) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// Warp fold of one row per lane into the 28 sums of the information form: entries 0..20 = upper triangle of g g^T
+// (row-major), 21..26 = g r, 27 = r r.  Reduce-scatter: the 32 (28 + 4 zero) products of every lane are halved five
+// times, each half travelling to the partner lane that owns it, so 31 shuffles replace 28 x 5; lane e ends up with the
+// total of entry e.  Fixed tree => deterministic.  Lanes without a measurement pass g = 0, r = 0.
+__device__ __forceinline__ double warp_fold_row(const double* g, double r) {
+  const int lane = threadIdx.x & 31;
+  double p[32];
+  {
+    int k = 0;
 #pragma unroll
-  for (int k = 0; k < kNAcc; ++k) {
-    double v = acc[k];
+    for (int a = 0; a < 6; ++a)
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-    if (lane == 0) sm.wacc[warp][k] = v;
+      for (int b = a; b < 6; ++b) p[k++] = g[a] * g[b];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) p[21 + a] = g[a] * r;
+    p[27] = r * r;
+    p[28] = p[29] = p[30] = p[31] = 0.0;
   }
 #pragma unroll
-  for (int m = 16; m > 0; m >>= 1) { cs += __shfl_xor_sync(0xffffffffu, cs, m); cc += __shfl_xor_sync(0xffffffffu, cc, m); }
-  if (lane == 0) { sm.wcnt[warp][0] = cs; sm.wcnt[warp][1] = cc; }
-  __syncthreads();
-  if (!finish) return;
-  if (threadIdx.x < kNAcc) {  // accumulates: callers zero sm.acc / sm.cnt at the start of a pass
-    double v = sm.acc[threadIdx.x];
-    for (int w = 0; w < kWarps; ++w) v += sm.wacc[w][threadIdx.x];
-    sm.acc[threadIdx.x] = v;
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const double send = up ? p[i] : p[i + h];
+      const double keep = up ? p[i + h] : p[i];
+      p[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    }
   }
-  if (threadIdx.x == 32) {
-    int a = sm.cnt[0], b = sm.cnt[1];
-    for (int w = 0; w < kWarps; ++w) { a += sm.wcnt[w][0]; b += sm.wcnt[w][1]; }
-    sm.cnt[0] = a; sm.cnt[1] = b;
-  }
-  __syncthreads();
+  return p[0];
 }
 
 __device__ __forceinline__ int col6(int a) { return a < 3 ? a : a + 3; }  // {0,1,2,6,7,8}
@@ -424,7 +366,7 @@ __device__ void form_M6(Smem& sm, double sig2, int idx, int stride) {
   for (int t = idx; t < 36; t += stride) {
     const int a = t / 6, c = t % 6;
     double s = 0;
-    for (int k = 0; k < 6; ++k) s += sm.A6[a * 6 + k] * sm.P[col6(k) * 18 + col6(c)];
+    for (int k = 0; k < 6; ++k) s += sm.A6[a * 6 + k] * sm.Pc[col6(k) * 6 + c];
     if (a == c) s += sig2;
     sm.M6[t] = s;
   }
@@ -503,17 +445,17 @@ __device__ bool warp_lu_cols(const double* S, double* B, int nrhs) {
   return true;
 }
 
-// sm.acc / sm.cnt += the per-warp partial sums of the last tile (block_reduce_acc with finish = false)
-__device__ __forceinline__ void finish_acc_warp0(Smem& sm) {
+// sm.acc / sm.cnt = the sums of the per-warp partial folds of this pass (nvw of them), in warp order
+__device__ __forceinline__ void finish_acc_warp0(Smem& sm, const double* wacc, const int* wcnt, int nvw) {
   const int lane = threadIdx.x & 31;
   if (lane < kNAcc) {
-    double v = sm.acc[lane];
-    for (int w = 0; w < kWarps; ++w) v += sm.wacc[w][lane];
+    double v = 0.0;
+    for (int w = 0; w < nvw; ++w) v += wacc[w * kNAcc + lane];
     sm.acc[lane] = v;
   } else if (lane < kNAcc + 2) {
     const int k = lane - kNAcc;
-    int a = sm.cnt[k];
-    for (int w = 0; w < kWarps; ++w) a += sm.wcnt[w][k];
+    int a = 0;
+    for (int w = 0; w < nvw; ++w) a += wcnt[w * 2 + k];
     sm.cnt[k] = a;
   }
   __syncwarp();
