@@ -215,6 +215,15 @@ void lins_oracle_boxminus(const double* a, const double* b, double* dx) {
   sa.boxMinus(sb, v);
   for (int i = 0; i < 18; ++i) dx[i] = v[i];
 }
+// form A gain alone (StateEstimator.hpp:542-546): H is M x 18 row-major, P 18 x 18 row-major, K out 18 x M row-major —
+// exposed so that tests can pin it against an independent Cholesky (scipy / LAPACK)
+void lins_oracle_gain_form_a(const double* H, int M, const double* P, double sig2, double* K) {
+  std::vector<double> h(H, H + (size_t)M * 18), k;
+  Mat18 Pm;
+  for (int a = 0; a < 18; ++a) for (int b = 0; b < 18; ++b) Pm.m[a][b] = P[a * 18 + b];
+  Estimator::gainFormA(h, M, Pm, sig2, k);
+  std::memcpy(K, k.data(), sizeof(double) * 18 * (size_t)M);
+}
 // de-skew helpers: mode 0 = transformToStart, 1 = transformToEnd
 void lins_oracle_transform(const lins_params* p, const double* lin_state, int mode, const lins_point* in, int n,
                            lins_point* out) {

@@ -49,6 +49,7 @@ def lib():
                                               C.c_int, vp, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.lins_oracle_sym_eig6.argtypes = [vp, vp, vp]
         L.lins_oracle_qr_solve6.argtypes = [vp, vp, vp]
+        L.lins_oracle_gain_form_a.argtypes = [vp, C.c_int, vp, C.c_double, vp]
         L.lins_oracle_boxplus.argtypes = [vp, vp, vp]
         L.lins_oracle_boxminus.argtypes = [vp, vp, vp]
         L.lins_oracle_transform.argtypes = [C.POINTER(LinsParams), vp, C.c_int, vp, C.c_int, vp]
