@@ -32,6 +32,7 @@
 #ifndef LINS_GPU_H_
 #define LINS_GPU_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -156,11 +157,23 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* batch);
 int lins_gpu_batch_run(lins_ctx* ctx);
 int lins_gpu_batch_download(lins_ctx* ctx, double* state_out /*n x 19*/, double* cov_out /*n x 324*/,
                             lins_scan_result* results /*n*/, lins_report* reports /*n, optional*/);
+/* The correspondence IDs the resident batch holds after a run — pointSearchSurfInd1/2/3 and pointSearchCornerInd1/2
+   (StateEstimator.hpp:1459-1465) of every unit's LAST search iteration, concatenated in batch order (3 per surf query,
+   2 per corner query, -1 = none).  Parity hook for the batched mode; either pointer may be NULL. */
+int lins_gpu_batch_download_indices(lins_ctx* ctx, int32_t* surf_ind, int32_t* corner_ind);
 /* upload + run + download in one call (the end-to-end entry point). */
 int lins_gpu_ieskf_batch(lins_ctx* ctx, const lins_batch_desc* batch, double* state_out, double* cov_out,
                          lins_scan_result* results);
 /* device pointer of the resident lins_scan_result array (n_scans x 64 B) for a zero-copy pose gather. */
 int lins_gpu_batch_results_device(lins_ctx* ctx, void** dev_ptr, int* n_scans);
+
+/* Optional: page-lock (pin) a host buffer the caller owns — a thin wrapper over cudaHostRegister so that a caller without
+   a CUDA binding of its own (the reference is plain C++ / ROS / PCL) can pin the storage of its point clouds once.
+   lins_gpu_batch_upload detects pinned clouds and then DMAs the raw 32-B records straight from the caller's memory and
+   packs them on the device: no host pass over the points (pageable clouds are packed by host threads into internal
+   pinned staging first).  Unregister before freeing the buffer. */
+int lins_gpu_host_register(void* ptr, size_t bytes);
+int lins_gpu_host_unregister(void* ptr);
 
 /* Split "Jacobian kernel" (SURVEY.md §8(d) unit U1): residual + Jacobian row + 29-scalar reduction over the
    resident batch given the correspondence IDs of iteration `iter` of each scan's current linearisation

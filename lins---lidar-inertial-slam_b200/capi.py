@@ -28,6 +28,7 @@ EXPORTS = [
     "lins_gpu_batch_upload", "lins_gpu_batch_run", "lins_gpu_batch_download", "lins_gpu_ieskf_batch",
     "lins_gpu_batch_results_device", "lins_gpu_batch_jacobian_pass", "lins_gpu_launch_count", "lins_gpu_sync",
     "lins_gpu_debug_phase_cycles", "lins_gpu_map_set", "lins_gpu_scan2map", "lins_gpu_map_associate",
+    "lins_gpu_host_register", "lins_gpu_host_unregister", "lins_gpu_batch_download_indices",
 ]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
@@ -81,12 +82,44 @@ def lib():
         L.lins_gpu_map_set.argtypes = [vp, vp, C.c_int, vp, C.c_int]
         L.lins_gpu_scan2map.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp, C.POINTER(LinsMapReport)]
         L.lins_gpu_map_associate.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp] + [vp] * 6
+        L.lins_gpu_host_register.argtypes = [vp, C.c_size_t]
+        L.lins_gpu_batch_download_indices.argtypes = [vp, vp, vp]
+        L.lins_gpu_host_unregister.argtypes = [vp]
         _LIB = L
     return _LIB
 
 
 class LinsError(RuntimeError):
     pass
+
+
+def pin_batch(batch: Batch):
+    """Page-lock the four cloud arrays of a host batch in place (lins_gpu_host_register): lins_gpu_batch_upload then DMAs
+    the raw records straight from them.  Returns the list of pinned arrays; call unpin_batch before they are freed."""
+    L = lib()
+    pinned = []
+    for k in Batch.FIELDS:
+        a = batch.clouds[k]
+        if a.nbytes == 0:
+            continue
+        rc = L.lins_gpu_host_register(a.ctypes.data, a.nbytes)
+        if rc != 0:
+            unpin_arrays(pinned)
+            raise LinsError(f"lins_gpu_host_register failed with {rc}")
+        pinned.append(a)
+    batch._pinned = pinned
+    return pinned
+
+
+def unpin_arrays(arrays):
+    L = lib()
+    for a in arrays:
+        L.lins_gpu_host_unregister(a.ctypes.data)
+
+
+def unpin_batch(batch: Batch):
+    unpin_arrays(getattr(batch, "_pinned", []))
+    batch._pinned = []
 
 
 class LinsGpu:
@@ -218,6 +251,13 @@ class LinsGpu:
         reps = (LinsReport * n)() if reports else None
         self._ck(self.L.lins_gpu_batch_download(self.h, ptr(so), ptr(co), ptr(res), C.cast(reps, C.c_void_p) if reports else None))
         return so, co, res, reps
+
+    def batch_download_indices(self, batch: Batch):
+        """(surf_ind (Ns_total, 3), corner_ind (Nc_total, 2)) of the resident batch's last search iteration."""
+        si = np.full((int(batch.offsets["surf_flat"][-1]), 3), -2, np.int32)
+        ci = np.full((int(batch.offsets["corner_sharp"][-1]), 2), -2, np.int32)
+        self._ck(self.L.lins_gpu_batch_download_indices(self.h, ptr(si), ptr(ci)))
+        return si, ci
 
     def ieskf_batch(self, batch: Batch, covs=True):
         """upload + run + download through host buffers: the end-to-end entry point."""

@@ -21,6 +21,14 @@ namespace lins_dev {
 #define LINS_SEARCH_DIAG 0
 #endif
 constexpr bool kSearchDiag = LINS_SEARCH_DIAG != 0;  // per-search cycle counters for tools/phase_profile.py
+// widest windows (azimuth bins per ring) a single thread scans in a unit's first pass; wider ones go to a warp
+#ifndef LINS_THREAD_SCAN_BINS
+#define LINS_THREAD_SCAN_BINS 16
+#endif
+#ifndef LINS_THREAD_WALK_BINS
+#define LINS_THREAD_WALK_BINS 48
+#endif
+constexpr int kThreadScanBins = LINS_THREAD_SCAN_BINS, kThreadWalkBins = LINS_THREAD_WALK_BINS;
 
 struct PassBuffers {           // per-query arrays, indexed by v = slot * qtile + i (shared memory, or the CTA's global scratch)
   float4* qpt;               // staged queries (x, y, z, intensity)
@@ -55,6 +63,7 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
   const int Q = bv.qtile, NQ = bv.nslots * Q;
   const float nearf = (float)kp.nearest_sq;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int toff = cta.pass_first ? 32 : 0;  // diagnostics: passes that contain a unit's first pass are clocked separately
 
   // ---- A2: de-skew, fused with phase P1 of the association (same thread-per-query mapping; P1 touches only its own
   // query's state and the read-only index): per-query level -2 everything certified, -3 closest point certified (walks
@@ -99,14 +108,18 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       if (ok1 && (ok2 || ccr0 < 0)) { pb.qw[v] = make_int4(-2, 0, 0, 0); continue; }
       if (ok1) { az_polar(s, qa); pb.qa[v] = qa; pb.qw[v] = make_int4(-3, 0, 0, 0); continue; }
     }
-    const int w1 = az_prepare_nn(ixq, s, nearf, seeded ? pb.pos[3 * v] : -1, qa);
+    const int w1 = az_prepare_nn(ixq, s, nearf, seeded ? pb.pos[3 * v] : -1, (int)pb.qpt[v].w, qa);
     pb.qa[v] = qa;
     pb.qw[v] = make_int4(w1, 0, 0, 0);
-    pb.wl[atomicAdd(&cta.wl_n[0], 1)] = v;  // (list order does not matter: every query's result goes to its own slot)
+    // (list order does not matter: every query's result goes to its own slot.)  Two lists share pb.wl: searches run by a
+    // warp each from the front, searches run by a thread each (small windows in a pass where the whole unit searches)
+    // from the back.
+    if (sm.first_pass && w1 >= 0 && (w1 & 0xffff) <= kThreadScanBins) pb.wl[NQ - 1 - atomicAdd(&cta.wl_tn[0], 1)] = v;
+    else pb.wl[atomicAdd(&cta.wl_n[0], 1)] = v;
     if (bv.timers && w1 >= 0) atomicAdd(&cta.dbg[0], w1 & 0xffff);
   }
   __syncthreads();
-  LINS_TICK(3);
+  LINS_TICK(3 + toff);
 
   if (cta.any_indexed) {
     // ---- A3/A4 fast path.  Scalar preparation (certificates, atan2f, asinf, bounds: P1 above, P3 below) runs one
@@ -116,6 +129,29 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       atomicAdd((unsigned long long*)&bv.timers[12], (unsigned long long)cta.dbg[0]);
     }
     const float gate = sqrtf(nearf);
+    // result of a closest-point search -> the query's state (one thread)
+    auto nn_finish = [&](int v, const AzIndex& ix, const float4 s, const Top3& top, int w1, float Bout) {
+      const unsigned long long k1 = top.k1;
+      const int p1 = top.p1;
+      const float d1 = __uint_as_float((unsigned)(k1 >> 32));
+      const bool acc1 = k1 != kKeyMax && p1 >= 0 && (double)d1 < kp.nearest_sq;
+      // accepted: what everything but the two front-runners exceeded; else the slack of "nothing within the gate"
+      const float bound1 = w1 < 0 ? -1.f : acc1 ? cert_bound(top.d3, Bout) : rejected_slack((unsigned)(k1 >> 32), Bout, gate);
+      pb.qref[v] = make_float4(s.x, s.y, s.z, bound1);
+      pb.qext[v].y = __int_as_float(acc1 ? top.p2 : -1);
+      pb.pos[3 * v] = acc1 ? p1 : -1;
+      pb.qccr[v] = acc1 ? ((slot_ring(ix.pts[p1].w) << 24) | (int)(unsigned)(k1 & 0xffffffffu)) : -1;
+    };
+    // P2, thread-level list first (a warp with no share of it goes straight to the warp-level list)
+    for (int k = threadIdx.x; k < cta.wl_tn[0]; k += kThreads) {
+      const int v = pb.wl[NQ - 1 - k];
+      const int sl = slot_of(v, Q), i = v - sl * Q;
+      const Smem& sm = slots[sl];
+      const AzIndex ix = az_index_of(sm, bv, i < sm.ns);
+      const float4 s = pb.sel[v];
+      const int w1 = pb.qw[v].x;
+      nn_finish(v, ix, s, az_scan_nn_thread(ix, s, w1), w1, pb.qa[v].w);
+    }
     // P2: warps pull queries from the work list (the per-query cost is heavy-tailed; a static split leaves warps idle)
     for (;;) {
       int k = 0;
@@ -126,8 +162,6 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       const int sl = slot_of(v, Q), i = v - sl * Q;
       const Smem& sm = slots[sl];
       int w1 = pb.qw[v].x;
-      unsigned long long k1 = kKeyMax;
-      int p1 = -1;
       Top3 top;
       top.init();
       const bool surf = i < sm.ns;
@@ -144,21 +178,11 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
           }
         }
         top = az_scan_nn(ix, s, w1);
-        k1 = top.k1; p1 = top.p1;
       }
-      if (lane == 0) {
-        const float d1 = __uint_as_float((unsigned)(k1 >> 32));
-        const bool acc1 = k1 != kKeyMax && p1 >= 0 && (double)d1 < kp.nearest_sq;
-        // accepted: what everything but the two front-runners exceeded; else the slack of "nothing within the gate"
-        const float bound1 = w1 < 0 ? -1.f : acc1 ? cert_bound(top.d3, qa.w) : rejected_slack((unsigned)(k1 >> 32), qa.w, gate);
-        pb.qref[v] = make_float4(s.x, s.y, s.z, bound1);
-        pb.qext[v].y = __int_as_float(acc1 ? top.p2 : -1);
-        pb.pos[3 * v] = acc1 ? p1 : -1;
-        pb.qccr[v] = acc1 ? ((slot_ring(ix.pts[p1].w) << 24) | (int)(unsigned)(k1 & 0xffffffffu)) : -1;
-      }
+      if (lane == 0) nn_finish(v, ix, s, top, w1, qa.w);
     }
     __syncthreads();
-    LINS_TICK(4);
+    LINS_TICK(4 + toff);
     for (int v = threadIdx.x; v < NQ; v += kThreads) {  // P3
       const int sl = slot_of(v, Q), i = v - sl * Q;
       const Smem& sm = slots[sl];
@@ -180,17 +204,45 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       const int sd2 = seeded ? pb.pos[3 * v + 1] : -1, sd3 = seeded ? pb.pos[3 * v + 2] : -1;
       const int c = ccr & 0x00ffffff, cr = (int)((unsigned)ccr >> 24);
       const AzIndex ix = az_index_of(sm, bv, surf);
-      if (surf) az_prepare_walk<true>(ix, pb.sel[v], pb.qa[v], c, cr, sd2, sd3, min(sm.ns, sm.Ts), nearf, w2, w3, B2, B3);
-      else az_prepare_walk<false>(ix, pb.sel[v], pb.qa[v], c, cr, sd2, sd3, min(sm.nc, sm.Tc), nearf, w2, w3, B2, B3);
+      const int p1 = pb.pos[3 * v];
+      if (surf) az_prepare_walk<true>(ix, pb.sel[v], pb.qa[v], p1, c, cr, sd2, sd3, min(sm.ns, sm.Ts), nearf, w2, w3, B2, B3);
+      else az_prepare_walk<false>(ix, pb.sel[v], pb.qa[v], p1, c, cr, sd2, sd3, min(sm.nc, sm.Tc), nearf, w2, w3, B2, B3);
       pb.qw[v] = make_int4(1, w2, w3, ccr);
       reinterpret_cast<float2*>(pb.key)[v] = make_float2(B2, B3);
-      pb.wl[atomicAdd(&cta.wl_n[1], 1)] = v;
+      if (sm.first_pass && (w2 & 0xffff) <= kThreadScanBins && (w3 & 0xffff) <= kThreadWalkBins) pb.wl[NQ - 1 - atomicAdd(&cta.wl_tn[1], 1)] = v;
+      else pb.wl[atomicAdd(&cta.wl_n[1], 1)] = v;
       if (bv.timers) atomicAdd(&cta.dbg[1], (w2 & 0xffff) + 4 * (w3 & 0xffff));
     }
     __syncthreads();
     if (bv.timers && threadIdx.x == 0) {
       atomicAdd((unsigned long long*)&bv.timers[11], (unsigned long long)cta.wl_n[1]);
       atomicAdd((unsigned long long*)&bv.timers[13], (unsigned long long)cta.dbg[1]);
+    }
+    // result of a query's walks -> its state + the correspondence IDs (one thread)
+    auto walk_finish = [&](int v, const Smem& sm, int i, bool surf, const float4 s, int ccr, const WalkOut& wo) {
+      pb.pos[3 * v + 1] = wo.pos2; pb.pos[3 * v + 2] = wo.pos3;
+      pb.qref2[v] = make_float4(s.x, s.y, s.z, wo.bound2);
+      float4 ex = pb.qext[v];  // (.y = the closest point's runner-up, written by P2 or kept from an earlier pass)
+      ex.x = wo.bound3; ex.z = __int_as_float(wo.run2); ex.w = __int_as_float(wo.run3);
+      pb.qext[v] = ex;
+      const int i1 = ccr & 0x00ffffff;
+      if (surf) { int* o = bv.ind_s + 3 * (size_t)(sm.qs0 + i); o[0] = i1; o[1] = wo.i2; o[2] = wo.i3; }
+      else { int* o = bv.ind_c + 2 * (size_t)(sm.qc0 + i - sm.ns); o[0] = i1; o[1] = wo.i2; }
+    };
+    // P4, thread-level list first.  :859 / :983 loop-bound quirk (+ OOB clamp): forward candidates count only below the
+    // QUERY count
+    for (int k = threadIdx.x; k < cta.wl_tn[1]; k += kThreads) {
+      const int v = pb.wl[NQ - 1 - k];
+      const int sl = slot_of(v, Q), i = v - sl * Q;
+      const Smem& sm = slots[sl];
+      const int4 w = pb.qw[v];
+      const bool surf = i < sm.ns;
+      const float2 B = reinterpret_cast<const float2*>(pb.key)[v];
+      const float4 s = pb.sel[v];
+      const AzIndex ix = az_index_of(sm, bv, surf);
+      const WalkOut wo = surf ? az_scan_walk_thread<true>(ix, s, w.w, w.y, w.z, min(sm.ns, sm.Ts), nearf, B.x, B.y)
+                              : az_scan_walk_thread<false>(ix, s, w.w, w.y, w.z, min(sm.nc, sm.Tc), nearf, B.x, B.y);
+      walk_finish(v, sm, i, surf, s, w.w, wo);
     }
     for (;;) {  // P4: same work-list scheme
       int k = 0;
@@ -206,19 +258,9 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       const int w2 = w.y, w3 = w.z;
       const float4 s = pb.sel[v];
       const AzIndex ix = az_index_of(sm, bv, surf);
-      // :859 / :983 loop-bound quirk (+ OOB clamp): forward candidates count only below the QUERY count
       const WalkOut wo = surf ? az_scan_walk<true>(ix, s, w.w, w2, w3, min(sm.ns, sm.Ts), nearf, B.x, B.y)
                               : az_scan_walk<false>(ix, s, w.w, w2, w3, min(sm.nc, sm.Tc), nearf, B.x, B.y);
-      if (lane == 0) {
-        pb.pos[3 * v + 1] = wo.pos2; pb.pos[3 * v + 2] = wo.pos3;
-        pb.qref2[v] = make_float4(s.x, s.y, s.z, wo.bound2);
-        float4 ex = pb.qext[v];  // (.y = the closest point's runner-up, written by P2 or kept from an earlier pass)
-        ex.x = wo.bound3; ex.z = __int_as_float(wo.run2); ex.w = __int_as_float(wo.run3);
-        pb.qext[v] = ex;
-        const int i1 = w.w & 0x00ffffff;
-        if (surf) { int* o = bv.ind_s + 3 * (size_t)(sm.qs0 + i); o[0] = i1; o[1] = wo.i2; o[2] = wo.i3; }
-        else { int* o = bv.ind_c + 2 * (size_t)(sm.qc0 + i - sm.ns); o[0] = i1; o[1] = wo.i2; }
-      }
+      if (lane == 0) walk_finish(v, sm, i, surf, s, w.w, wo);
     }
   }
   if (cta.any_legacy) {
@@ -261,9 +303,9 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
     }
   }
   __syncthreads();
-  LINS_TICK(5);
+  LINS_TICK(5 + toff);
   // the searches of this pass are over: reset the work lists for the next pass
-  if (threadIdx.x == kThreads - 1) { cta.wl_n[0] = 0; cta.wl_n[1] = 0; cta.wl_head[0] = 0; cta.wl_head[1] = 0; cta.dbg[0] = 0; cta.dbg[1] = 0; }
+  if (threadIdx.x == kThreads - 1) { cta.wl_n[0] = 0; cta.wl_n[1] = 0; cta.wl_tn[0] = 0; cta.wl_tn[1] = 0; cta.wl_head[0] = 0; cta.wl_head[1] = 0; cta.dbg[0] = 0; cta.dbg[1] = 0; }
 
   // ---- A5/A6 residuals + A7-A9 fold ------------------------------------------------------------------------------
   // tripod points: slots of the sorted copies after a fast-path search, otherwise original indices into the walk clouds.
@@ -322,7 +364,7 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
     }
   }
   __syncthreads();
-  LINS_TICK(6);
+  LINS_TICK(6 + toff);
 }
 
 }  // namespace lins_dev

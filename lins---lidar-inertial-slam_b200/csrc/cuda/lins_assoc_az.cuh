@@ -157,12 +157,37 @@ __device__ __forceinline__ float az_seed_bound(const AzIndex& ix, const float4 s
   }
   return U1;
 }
-__device__ __forceinline__ int az_prepare_nn(const AzIndex& ix, const float4 s, float nearf, int seed_slot, float4& qa) {
+__device__ __forceinline__ int az_bin_of_angle(float a, int nb) {
+  const int b = (int)floorf((a + kPiF) * ((float)nb * (0.5f / kPiF)));
+  return min(max(b, 0), nb - 1);
+}
+// Unseeded query (a unit's first pass): bound from a few real targets next to the query in the index — the buckets
+// around the query's azimuth on the ring the query itself was measured on (ring_guess = int(intensity) of the raw query;
+// the last scan has the same rings), then on the two adjacent rings when that found nothing within a metre.  Any real
+// target's distance is a valid upper bound on the minimum, so this only narrows the window (exactness is untouched).
+__device__ __forceinline__ float az_bucket_bound(const AzIndex& ix, const float4 s, float az, int ring_guess, float U1) {
+  const int bq = az_bin_of_angle(az, ix.nb);
+  const int r0 = min(max(ring_guess, 0), ix.nrings - 1);
+#pragma unroll 1
+  for (int k = 0; k < 3; ++k) {
+    const int r = k == 0 ? r0 : (k == 1 ? r0 - 1 : r0 + 1);
+    if (k == 1 && U1 < 1.0f) break;
+    if (r < 0 || r >= ix.nrings) continue;
+    const int base = r * ix.nb;
+    int p = ix.bstart[base + max(bq - 1, 0)];
+    const int pe = min((int)ix.bstart[base + min(bq + 2, ix.nb)], p + 4);
+    for (; p < pe; ++p) U1 = az_seed_bound(ix, s, p, U1);
+  }
+  return U1;
+}
+__device__ __forceinline__ int az_prepare_nn(const AzIndex& ix, const float4 s, float nearf, int seed_slot, int ring_guess, float4& qa) {
   qa = make_float4(0.f, 0.f, -1.f, 0.f);
   if (!(s.x == s.x && s.y == s.y && s.z == s.z) || ix.T <= 0) return -1;
   az_polar(s, qa);
   // nothing beyond the gate can be accepted (StateEstimator.hpp:851)
-  return az_nn_window(ix, az_seed_bound(ix, s, seed_slot, nearf), qa);
+  float U1 = az_seed_bound(ix, s, seed_slot, nearf);
+  if (seed_slot < 0) U1 = az_bucket_bound(ix, s, qa.x, ring_guess, U1);
+  return az_nn_window(ix, U1, qa);
 }
 // Probe radius: a search whose window (built from the gate, i.e. without a usable previous answer) is much wider
 // than the window of this radius first scans the small window; the best candidate found there is a real target,
@@ -278,6 +303,34 @@ __device__ __forceinline__ Top3 az_scan_nn(const AzIndex& ix, const float4 s, in
   return az_scan_nn_t<1>(ix, s, win, tm);
 }
 
+// One THREAD per query: the same scan, sequential.  Used where (nearly) every query of a unit searches at once — a
+// unit's first pass — and the windows are small (index-neighbourhood seeds, az_bucket_bound): a warp per query would
+// spend most of its lanes on empty slices there, a thread per query keeps all 32 lanes on real candidates.  Keys are
+// unique ((distance, index) / (distance, visiting order)), so the two front-runners and the third distance do not
+// depend on the visiting order: results are identical to the warp scan by construction.
+__device__ __forceinline__ void az_scan_slice_thread(const AzIndex& ix, const float4 s, int p, int pe, Top3& top) {
+  for (; p < pe; p += 2) {  // two loads in flight
+    const float4 t0 = ld_slot(ix, p), t1 = ld_slot(ix, p + 1 < pe ? p + 1 : p);
+    const unsigned d0 = __float_as_uint(sqdist_f32(s.x, s.y, s.z, t0.x, t0.y, t0.z));
+    const unsigned d1 = __float_as_uint(sqdist_f32(s.x, s.y, s.z, t1.x, t1.y, t1.z));
+    top.insert(((unsigned long long)d0 << 32) | (unsigned)slot_index(t0.w), p);
+    top.insert(p + 1 < pe ? (((unsigned long long)d1 << 32) | (unsigned)slot_index(t1.w)) : kKeyMax, p + 1);
+  }
+}
+__device__ __forceinline__ Top3 az_scan_nn_thread(const AzIndex& ix, const float4 s, int win) {
+  const int blo = win >> 16, nbins = win & 0xffff;
+  const int e0 = min(blo + nbins, ix.nb), e1 = blo + nbins - ix.nb;
+  Top3 top;
+  top.init();
+  for (int r = 0; r < ix.nrings; ++r) {
+    const int base = r * ix.nb;
+    az_scan_slice_thread(ix, s, ix.bstart[base + blo], ix.bstart[base + e0], top);
+    if (e1 > 0) az_scan_slice_thread(ix, s, ix.bstart[base], ix.bstart[base + e1], top);
+  }
+  if ((unsigned)(top.k1 >> 32) >= 0x7f800000u) { top.k1 = kKeyMax; top.p1 = -1; }  // only inf / NaN distances: nothing found
+  return top;
+}
+
 // ---- phase P3 (one THREAD per query): bound + window the walks of a query whose closest point is (c, cr) -------
 // w2 / w3 = windows of the Ind2 / Ind3 searches, B2 / B3 = distance bound of everything outside them
 // bound from a candidate slot while it is an admissible candidate of THIS search (CLS2: the Ind2 search)
@@ -293,11 +346,31 @@ __device__ __forceinline__ float walk_seed_bound(const AzIndex& ix, const float4
 }
 // Uinit = NEAREST_FEATURE_SEARCH_SQ_DIST: nothing beyond the gate is accepted
 template <bool SURF>
-__device__ __forceinline__ void az_prepare_walk(const AzIndex& ix, const float4 s, const float4 qa, int c, int cr, int seed2,
+__device__ __forceinline__ void az_prepare_walk(const AzIndex& ix, const float4 s, const float4 qa, int p1, int c, int cr, int seed2,
                                                 int seed3, int fwdBound, float Uinit, int& w2, int& w3, float& B2, float& B3) {
-  // bounds from the previous answers
-  const float U2 = walk_seed_bound<SURF, true>(ix, s, seed2, c, cr, fwdBound, Uinit);
-  const float U3 = SURF ? walk_seed_bound<SURF, false>(ix, s, seed3, c, cr, fwdBound, Uinit) : Uinit;
+  // bounds from the previous answers ...
+  float U2 = walk_seed_bound<SURF, true>(ix, s, seed2, c, cr, fwdBound, Uinit);
+  float U3 = SURF ? walk_seed_bound<SURF, false>(ix, s, seed3, c, cr, fwdBound, Uinit) : Uinit;
+  // ... and from the index neighbourhood of the closest point / of the query's azimuth on the adjacent rings.  Each is
+  // used only while it is an admissible candidate of the search it bounds (walk_seed_bound), so the windows shrink
+  // (a unit's first pass has no previous answers: gate-wide windows otherwise) and exactness is untouched.
+  if (SURF) {
+#pragma unroll
+    for (int d = -2; d <= 2; ++d)
+      if (d != 0) U2 = walk_seed_bound<true, true>(ix, s, p1 + d, c, cr, fwdBound, U2);
+  }
+  {
+    const int bq = az_bin_of_angle(qa.x, ix.nb);
+    float& U = SURF ? U3 : U2;
+#pragma unroll
+    for (int dr = -2; dr <= 2; ++dr) {
+      const int r = cr + dr;
+      if (dr == 0 || r < 0 || r >= ix.nrings) continue;
+      const int slot = ix.bstart[r * ix.nb + bq];
+      U = walk_seed_bound<SURF, !SURF>(ix, s, slot, c, cr, fwdBound, U);
+      U = walk_seed_bound<SURF, !SURF>(ix, s, slot - 1, c, cr, fwdBound, U);
+    }
+  }
   int blo, nbins;
   const float Uw2 = widen(U2);
   az_window(ix.nb, qa.x, az_halfwidth(Uw2, qa.y), blo, nbins);
@@ -374,6 +447,57 @@ __device__ __forceinline__ WalkOut az_scan_walk(const AzIndex& ix, const float4 
   };
   finish(mine2 ? top : neutral, B2, o.i2, o.pos2, o.run2, o.bound2);
   if (SURF) finish(mine2 ? neutral : top, B3, o.i3, o.pos3, o.run3, o.bound3);
+  else { o.i3 = -1; o.pos3 = -1; o.run3 = -1; o.bound3 = 0.f; }
+  return o;
+}
+
+// the same walks by ONE thread (see az_scan_nn_thread)
+template <bool SURF>
+__device__ __forceinline__ WalkOut az_scan_walk_thread(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
+                                                       float B2, float B3) {
+  const int c = ccr & 0x00ffffff, cr = (int)((unsigned)ccr >> 24);
+  Top3 t2, t3;
+  t2.init(); t3.init();
+#pragma unroll
+  for (int dr = -2; dr <= 2; ++dr) {
+    const int r = cr + dr;
+    const bool cls2 = SURF ? (dr == 0) : true;
+    if (r < 0 || r >= ix.nrings || (!SURF && dr == 0)) continue;
+    const int win = cls2 ? w2 : w3;
+    const int blo = win >> 16, nbins = win & 0xffff, base = r * ix.nb;
+    for (int seg = 0; seg < 2; ++seg) {
+      int p, pe;
+      if (seg == 0) { p = ix.bstart[base + blo]; pe = ix.bstart[base + min(blo + nbins, ix.nb)]; }
+      else { const int e1 = blo + nbins - ix.nb; if (e1 <= 0) break; p = ix.bstart[base]; pe = ix.bstart[base + e1]; }
+      for (; p < pe; p += 2) {
+        float4 tt[2];
+        tt[0] = ld_slot(ix, p); tt[1] = ld_slot(ix, p + 1 < pe ? p + 1 : p);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int pu = p + u;
+          const float4 t = tt[u];
+          const unsigned d = __float_as_uint(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z));
+          const int j = slot_index(t.w);
+          const bool fwd = j > c;
+          const bool adm = pu < pe && j != c && (!fwd || j < fwdBound);
+          const unsigned long long k = adm ? (((unsigned long long)d << 32) | (fwd ? order_fwd(j) : order_bwd(j))) : kKeyMax;
+          if (cls2) t2.insert(k, pu); else t3.insert(k, pu);
+        }
+      }
+    }
+  }
+  const float gate = sqrtf(nearf);
+  const unsigned nearbits = __float_as_uint(nearf);
+  WalkOut o;
+  auto finish = [&](const Top3& t, float Bout, int& idx, int& pos, int& run, float& bound) {
+    const bool ok = (unsigned)(t.k1 >> 32) < nearbits && t.p1 >= 0;
+    idx = ok ? order_decode((unsigned)(t.k1 & 0xffffffffu)) : -1;
+    pos = ok ? t.p1 : -1;
+    run = ok ? t.p2 : -1;
+    bound = ok ? cert_bound(t.d3, Bout) : rejected_slack((unsigned)(t.k1 >> 32), Bout, gate);
+  };
+  finish(t2, B2, o.i2, o.pos2, o.run2, o.bound2);
+  if (SURF) finish(t3, B3, o.i3, o.pos3, o.run3, o.bound3);
   else { o.i3 = -1; o.pos3 = -1; o.run3 = -1; o.bound3 = 0.f; }
   return o;
 }

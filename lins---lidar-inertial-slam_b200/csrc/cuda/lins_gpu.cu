@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lins_ieskf_kernel(const __
   if (tid == 0) {
     mbar_init(&cta.mbar, 1);
     cta.phase = 0;
-    cta.wl_n[0] = 0; cta.wl_n[1] = 0; cta.wl_head[0] = 0; cta.wl_head[1] = 0; cta.dbg[0] = 0; cta.dbg[1] = 0;  // (reset after every pass)
+    cta.wl_n[0] = 0; cta.wl_n[1] = 0; cta.wl_tn[0] = 0; cta.wl_tn[1] = 0; cta.wl_head[0] = 0; cta.wl_head[1] = 0; cta.dbg[0] = 0; cta.dbg[1] = 0;  // (reset after every pass)
     cta.exhausted = 0; cta.any_finished = 0;
     for (int s = 0; s < S; ++s) { slots[s].scan = -1; slots[s].fresh = 0; slots[s].run = 0; slots[s].finished = 0; }
     fence_mbar_init();
@@ -299,6 +299,13 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lins_ieskf_kernel(const __
         if (sm.fresh) ++nfresh;
       }
       cta.n_active = nact; cta.any_fresh = nfresh;
+      cta.pass_first = 0;
+      if (bv.timers) {  // diagnostics: does this pass contain a unit's first pass (every query searches)?
+        int nrun = 0;
+        for (int s = 0; s < S; ++s) { if (slots[s].fresh || (slots[s].run && slots[s].first_pass)) cta.pass_first = 1; if (slots[s].scan >= 0) ++nrun; }
+        atomicAdd((unsigned long long*)&bv.timers[cta.pass_first ? 62 : 30], 1ull);
+        atomicAdd((unsigned long long*)&bv.timers[cta.pass_first ? 63 : 31], (unsigned long long)nrun);
+      }
     }
     __syncthreads();
     if (cta.n_active == 0) {
@@ -461,6 +468,16 @@ __global__ void lins_transform_to_end_kernel(float4* __restrict__ pts, int n, co
   pts[i] = p;
 }
 
+// pcl::PointXYZI records (32 B) -> packed (x, y, z, intensity) (16 B) on the device: the upload path of clouds that
+// sit in caller-pinned host memory (DMA of the raw records, no host pass over the points).
+__global__ void lins_pack_points_kernel(const float4* __restrict__ raw, float4* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(raw + 2 * i);       // x y z pad
+    const float b = __ldcs(&raw[2 * i + 1].x);  // intensity
+    out[i] = make_float4(a.x, a.y, a.z, b);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host-side helpers
 // ---------------------------------------------------------------------------------------------------------
@@ -500,6 +517,7 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   size_t nqs = 0, nqc = 0, nts = 0, ntc = 0;
   int max_q = 0;
   DevBuf<float4> qs, qc, ts, tc, az_s, az_c;
+  DevBuf<float4> raw;              // raw 32-B records of clouds uploaded straight from caller-pinned memory (2 float4 per point)
   DevBuf<unsigned char> qscratch;  // per-CTA per-query arrays of units too large for shared memory
   int max_ts = 0, max_tc = 0;
   DevBuf<int> qs_off, qc_off, ts_off, tc_off, ind_s, ind_c, counter;
@@ -515,7 +533,7 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   PinBuf<lins_scan_result> h_results;
   PinBuf<lins_report> h_reports;
   void release() {
-    qs.release(); qc.release(); ts.release(); tc.release(); az_s.release(); az_c.release(); qscratch.release(); qs_off.release(); qc_off.release(); ts_off.release();
+    qs.release(); qc.release(); ts.release(); tc.release(); az_s.release(); az_c.release(); raw.release(); qscratch.release(); qs_off.release(); qc_off.release(); ts_off.release();
     tc_off.release(); ind_s.release(); ind_c.release(); counter.release(); state_in.release(); cov_in.release();
     state_out.release(); cov_out.release(); accum.release(); results.release(); reports.release(); sel_s.release();
     sel_c.release(); coeff_s.release(); coeff_c.release(); mask_s.release(); mask_c.release(); h_pts.release();
@@ -924,12 +942,41 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
   size_t seg[5] = {0, r.nqs, r.nqs + r.nqc, r.nqs + r.nqc + r.nts, total};
   float4* dsts[4] = {r.qs.p, r.qc.p, r.ts.p, r.tc.p};
   int* doffs[4] = {r.qs_off.p, r.qc_off.p, r.ts_off.p, r.tc_off.p};
+  // Clouds in caller-PINNED host memory (cudaHostAlloc / cudaHostRegister): the copy engine reads the raw 32-B records
+  // straight from the caller's buffer and a device kernel packs them — no host pass over the points at all (twice the
+  // PCIe bytes, zero host memory traffic besides the DMA reads; what makes a many-GPU host scale).  LINS_UPLOAD=pack
+  // forces the host-pack path, LINS_UPLOAD=pinned fails the call when a cloud is not pinned.
+  bool direct[4] = {false, false, false, false};
+  {
+    const char* mode = std::getenv("LINS_UPLOAD");
+    const bool force_pack = mode && std::strcmp(mode, "pack") == 0;
+    for (int k = 0; k < 4 && !force_pack; ++k) {
+      if (seg[k + 1] == seg[k]) continue;
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, pts[k]) == cudaSuccess && at.type == cudaMemoryTypeHost) direct[k] = true;
+      else cudaGetLastError();
+      if (!direct[k] && mode && std::strcmp(mode, "pinned") == 0) return fail(ctx, LINS_E_INVALID, "LINS_UPLOAD=pinned but a cloud is not in pinned host memory");
+    }
+    if (direct[0] || direct[1] || direct[2] || direct[3]) CK(r.raw.reserve(2 * total + 2));
+    for (int k = 0; k < 4; ++k) {
+      if (!direct[k]) continue;
+      const size_t cnt = seg[k + 1] - seg[k];
+      float4* rawk = r.raw.p + 2 * seg[k];
+      CK(cudaMemcpyAsync(rawk, pts[k], sizeof(lins_point) * cnt, cudaMemcpyHostToDevice, ctx->stream));
+      const int blocks = (int)std::min<size_t>((cnt + 255) / 256, (size_t)ctx->sm_count * 8);
+      lins_pack_points_kernel<<<blocks, 256, 0, ctx->stream>>>(rawk, dsts[k], cnt);
+      CK(cudaGetLastError());
+      ctx->launches += 1;
+    }
+  }
   {
     struct Slice { int k; size_t a, b; };
     std::vector<Slice> slices;
     const size_t SL = 1u << 16;
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 4; ++k) {
+      if (direct[k]) continue;
       for (size_t a = 0; a < seg[k + 1] - seg[k]; a += SL) slices.push_back(Slice{k, a, std::min(a + SL, seg[k + 1] - seg[k])});
+    }
     std::atomic<size_t> next(0);
     std::atomic<int> cuda_err(0);
     const int device = ctx->device;
@@ -952,7 +999,7 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
     if (const char* e = std::getenv("LINS_PACK_THREADS")) { const int v = std::atoi(e); if (v >= 1) want = std::min(v, 64); }
     int nthr = (int)std::min<size_t>((size_t)want, std::max<size_t>(slices.size(), 1));
     if (nthr < 1) nthr = 1;
-    ctx->pool.run(nthr, worker);
+    if (!slices.empty()) ctx->pool.run(nthr, worker);
     if (cuda_err.load() != 0) return fail(ctx, LINS_E_CUDA, "H2D copy of a packed slice", (cudaError_t)cuda_err.load());
   }
   for (int k = 0; k < 4; ++k) std::memcpy(r.h_off.p + (size_t)k * (n + 1), offs[k], sizeof(int) * (n + 1));
@@ -998,6 +1045,17 @@ int lins_gpu_batch_download(lins_ctx* ctx, double* state_out, double* cov_out, l
   if (cov_out) std::memcpy(cov_out, r.h_cov_out.p, sizeof(double) * 324 * n);
   if (results) std::memcpy(results, r.h_results.p, sizeof(lins_scan_result) * n);
   if (reports) std::memcpy(reports, r.h_reports.p, sizeof(lins_report) * n);
+  return LINS_OK;
+}
+
+int lins_gpu_batch_download_indices(lins_ctx* ctx, int32_t* surf_ind, int32_t* corner_ind) {
+  if (!ctx) return LINS_E_INVALID;
+  Resident& r = ctx->batch;
+  if (r.n <= 0) return fail(ctx, LINS_E_INVALID, "no resident batch");
+  CK(cudaSetDevice(ctx->device));
+  if (surf_ind && r.nqs) CK(cudaMemcpyAsync(surf_ind, r.ind_s.p, sizeof(int32_t) * 3 * r.nqs, cudaMemcpyDeviceToHost, ctx->stream));
+  if (corner_ind && r.nqc) CK(cudaMemcpyAsync(corner_ind, r.ind_c.p, sizeof(int32_t) * 2 * r.nqc, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return LINS_OK;
 }
 
@@ -1181,6 +1239,19 @@ int lins_gpu_map_associate(lins_ctx* ctx, const lins_point* corner, int nc, cons
   if (cmask && nc) CK(cudaMemcpyAsync(cmask, m.mask_c.p, (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
   if (smask && ns) CK(cudaMemcpyAsync(smask, m.mask_s.p, (size_t)ns, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return LINS_OK;
+}
+
+int lins_gpu_host_register(void* ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return LINS_E_INVALID;
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? LINS_E_NODEVICE : LINS_E_CUDA; }
+  return LINS_OK;
+}
+int lins_gpu_host_unregister(void* ptr) {
+  if (!ptr) return LINS_E_INVALID;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return LINS_E_CUDA; }
   return LINS_OK;
 }
 

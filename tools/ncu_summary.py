@@ -18,6 +18,7 @@ def main(rep, out_csv, key):
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     traffic = 0.0
+    inst = dur_ms = None
     with open(out_csv, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["metric", "unit", "value"])
@@ -26,9 +27,17 @@ def main(rep, out_csv, key):
                 w.writerow([h, u, v])
             if h in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 traffic += float(v) * SCALE[u]
+            if h == "smsp__inst_executed.sum":
+                inst = float(v.replace(",", ""))
+            if h == "gpu__time_duration.sum":
+                dur_ms = float(v.replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(u, 1.0)
     tj = os.path.join(os.path.dirname(out_csv), "traffic.json")
     d = json.load(open(tj)) if os.path.exists(tj) else {}
     d[key] = {"dram_bytes_per_launch": traffic, "source": os.path.basename(out_csv)}
+    if inst is not None:
+        d[key]["warp_instructions_per_launch"] = inst  # smsp__inst_executed.sum: bench.py's issue roofline
+    if dur_ms is not None:
+        d[key]["duration_ms_under_ncu"] = dur_ms
     json.dump(d, open(tj, "w"), indent=1, sort_keys=True)
     print(key, "traffic per launch: %.1f MB" % (traffic / 1e6), "->", out_csv)
 
