@@ -374,7 +374,14 @@ def main():
             capi.unpin_batch(b)
     b0 = batches[0]
     pts = sum(int(b0.offsets[k][-1]) for k in b0.FIELDS)
-    h2d = (32 if e2e_pinned else 16) * pts + 4 * 4 * (n + 1) + n * (20 + 324) * 8
+    # the library's default policy: caller-pinned clouds are DMA'd raw (32 B / point, packed on the device) when a context has
+    # fewer than 8 host pack threads to itself, otherwise host threads pack them to 16 B / point into pinned staging
+    pack_threads = int(os.environ.get("LINS_PACK_THREADS", "8"))
+    forced = os.environ.get("LINS_UPLOAD")
+    direct = e2e_pinned and (forced in ("direct", "pinned") or (forced is None and pack_threads < 8))
+    upload_mode = ("caller-pinned 32-B PointXYZI clouds: raw DMA + device pack (no host pass over the points)" if direct else
+                   f"32-B PointXYZI clouds packed to 16 B by {pack_threads} host threads per context into pinned staging")
+    h2d = (32 if direct else 16) * pts + 4 * 4 * (n + 1) + n * (20 + 324) * 8
     d2h = n * ((20 + 324) * 8 + 64)
 
     if rank != 0:
@@ -544,7 +551,7 @@ def main():
         "streams": f"one CUDA stream per resident batch ({NB}): consecutive steps overlap at their kernel tails; e2e = {NE} host threads, one context (and stream) each",
         "clocks": clk,
         "e2e": {"value": e2e_iters / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "host_threads": NE,
-                "upload": "caller-pinned 32-B PointXYZI clouds, raw DMA + device pack" if e2e_pinned else "pageable clouds, host pack threads -> pinned staging"},
+                "upload": upload_mode},
         "gpu_launches": int(total_launches),
         "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_jacobian": roofline_j, "mapping_refinement": mapping,
     }

@@ -21,7 +21,11 @@ namespace lins_dev {
 #define LINS_SEARCH_DIAG 0
 #endif
 constexpr bool kSearchDiag = LINS_SEARCH_DIAG != 0;  // per-search cycle counters for tools/phase_profile.py
-// widest windows (azimuth bins per ring) a single thread scans in a unit's first pass; wider ones go to a warp
+// widest windows (azimuth bins per ring) a group of kGroupLanes lanes scans; wider ones go to a whole warp
+#ifndef LINS_GROUP_LANES
+#define LINS_GROUP_LANES 4
+#endif
+constexpr int kGroupLanes = LINS_GROUP_LANES;
 #ifndef LINS_THREAD_SCAN_BINS
 #define LINS_THREAD_SCAN_BINS 16
 #endif
@@ -112,8 +116,9 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
     pb.qa[v] = qa;
     pb.qw[v] = make_int4(w1, 0, 0, 0);
     // (list order does not matter: every query's result goes to its own slot.)  Two lists share pb.wl: searches run by a
-    // warp each from the front, searches run by a thread each (small windows in a pass where the whole unit searches)
-    // from the back.
+    // warp each from the front, searches run by a group of kGroupLanes lanes each from the back.  Groups serve the pass in
+    // which (nearly) every query of a unit searches — its first — where throughput counts (measured: 1.5x faster there);
+    // the handful of searches of a later pass are latency bound and finish sooner with a warp each.
     if (sm.first_pass && w1 >= 0 && (w1 & 0xffff) <= kThreadScanBins) pb.wl[NQ - 1 - atomicAdd(&cta.wl_tn[0], 1)] = v;
     else pb.wl[atomicAdd(&cta.wl_n[0], 1)] = v;
     if (bv.timers && w1 >= 0) atomicAdd(&cta.dbg[0], w1 & 0xffff);
@@ -142,15 +147,24 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       pb.pos[3 * v] = acc1 ? p1 : -1;
       pb.qccr[v] = acc1 ? ((slot_ring(ix.pts[p1].w) << 24) | (int)(unsigned)(k1 & 0xffffffffu)) : -1;
     };
-    // P2, thread-level list first (a warp with no share of it goes straight to the warp-level list)
-    for (int k = threadIdx.x; k < cta.wl_tn[0]; k += kThreads) {
+    // P2, group-level list first: groups of kGroupLanes lanes pull queries (a warp whose groups find the list empty goes
+    // straight to the warp-level list)
+    constexpr int G = kGroupLanes;
+    const int sub = lane & (G - 1), glead = lane & ~(G - 1);
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << glead);
+    for (;;) {
+      int k = 0;
+      if (sub == 0) k = atomicAdd(&cta.wl_thead[0], 1);
+      k = __shfl_sync(gmask, k, glead);
+      if (k >= cta.wl_tn[0]) break;
       const int v = pb.wl[NQ - 1 - k];
       const int sl = slot_of(v, Q), i = v - sl * Q;
       const Smem& sm = slots[sl];
       const AzIndex ix = az_index_of(sm, bv, i < sm.ns);
       const float4 s = pb.sel[v];
       const int w1 = pb.qw[v].x;
-      nn_finish(v, ix, s, az_scan_nn_thread(ix, s, w1), w1, pb.qa[v].w);
+      const Top3 top = az_scan_nn_group<G>(ix, s, w1, sub, gmask);
+      if (sub == 0) nn_finish(v, ix, s, top, w1, pb.qa[v].w);
     }
     // P2: warps pull queries from the work list (the per-query cost is heavy-tailed; a static split leaves warps idle)
     for (;;) {
@@ -209,7 +223,7 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       else az_prepare_walk<false>(ix, pb.sel[v], pb.qa[v], p1, c, cr, sd2, sd3, min(sm.nc, sm.Tc), nearf, w2, w3, B2, B3);
       pb.qw[v] = make_int4(1, w2, w3, ccr);
       reinterpret_cast<float2*>(pb.key)[v] = make_float2(B2, B3);
-      if (sm.first_pass && (w2 & 0xffff) <= kThreadScanBins && (w3 & 0xffff) <= kThreadWalkBins) pb.wl[NQ - 1 - atomicAdd(&cta.wl_tn[1], 1)] = v;
+      if (sm.first_pass && (w2 & 0xffff) <= kThreadWalkBins && (w3 & 0xffff) <= kThreadWalkBins) pb.wl[NQ - 1 - atomicAdd(&cta.wl_tn[1], 1)] = v;
       else pb.wl[atomicAdd(&cta.wl_n[1], 1)] = v;
       if (bv.timers) atomicAdd(&cta.dbg[1], (w2 & 0xffff) + 4 * (w3 & 0xffff));
     }
@@ -229,9 +243,13 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       if (surf) { int* o = bv.ind_s + 3 * (size_t)(sm.qs0 + i); o[0] = i1; o[1] = wo.i2; o[2] = wo.i3; }
       else { int* o = bv.ind_c + 2 * (size_t)(sm.qc0 + i - sm.ns); o[0] = i1; o[1] = wo.i2; }
     };
-    // P4, thread-level list first.  :859 / :983 loop-bound quirk (+ OOB clamp): forward candidates count only below the
+    // P4, group-level list first.  :859 / :983 loop-bound quirk (+ OOB clamp): forward candidates count only below the
     // QUERY count
-    for (int k = threadIdx.x; k < cta.wl_tn[1]; k += kThreads) {
+    for (;;) {
+      int k = 0;
+      if (sub == 0) k = atomicAdd(&cta.wl_thead[1], 1);
+      k = __shfl_sync(gmask, k, glead);
+      if (k >= cta.wl_tn[1]) break;
       const int v = pb.wl[NQ - 1 - k];
       const int sl = slot_of(v, Q), i = v - sl * Q;
       const Smem& sm = slots[sl];
@@ -240,9 +258,9 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       const float2 B = reinterpret_cast<const float2*>(pb.key)[v];
       const float4 s = pb.sel[v];
       const AzIndex ix = az_index_of(sm, bv, surf);
-      const WalkOut wo = surf ? az_scan_walk_thread<true>(ix, s, w.w, w.y, w.z, min(sm.ns, sm.Ts), nearf, B.x, B.y)
-                              : az_scan_walk_thread<false>(ix, s, w.w, w.y, w.z, min(sm.nc, sm.Tc), nearf, B.x, B.y);
-      walk_finish(v, sm, i, surf, s, w.w, wo);
+      const WalkOut wo = surf ? az_scan_walk_group<true, G>(ix, s, w.w, w.y, w.z, min(sm.ns, sm.Ts), nearf, B.x, B.y, sub, gmask)
+                              : az_scan_walk_group<false, G>(ix, s, w.w, w.y, w.z, min(sm.nc, sm.Tc), nearf, B.x, B.y, sub, gmask);
+      if (sub == 0) walk_finish(v, sm, i, surf, s, w.w, wo);
     }
     for (;;) {  // P4: same work-list scheme
       int k = 0;
@@ -305,7 +323,7 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
   __syncthreads();
   LINS_TICK(5 + toff);
   // the searches of this pass are over: reset the work lists for the next pass
-  if (threadIdx.x == kThreads - 1) { cta.wl_n[0] = 0; cta.wl_n[1] = 0; cta.wl_tn[0] = 0; cta.wl_tn[1] = 0; cta.wl_head[0] = 0; cta.wl_head[1] = 0; cta.dbg[0] = 0; cta.dbg[1] = 0; }
+  if (threadIdx.x == kThreads - 1) { cta.wl_n[0] = 0; cta.wl_n[1] = 0; cta.wl_tn[0] = 0; cta.wl_tn[1] = 0; cta.wl_head[0] = 0; cta.wl_head[1] = 0; cta.wl_thead[0] = 0; cta.wl_thead[1] = 0; cta.dbg[0] = 0; cta.dbg[1] = 0; }
 
   // ---- A5/A6 residuals + A7-A9 fold ------------------------------------------------------------------------------
   // tripod points: slots of the sorted copies after a fast-path search, otherwise original indices into the walk clouds.

@@ -303,30 +303,47 @@ __device__ __forceinline__ Top3 az_scan_nn(const AzIndex& ix, const float4 s, in
   return az_scan_nn_t<1>(ix, s, win, tm);
 }
 
-// One THREAD per query: the same scan, sequential.  Used where (nearly) every query of a unit searches at once — a
-// unit's first pass — and the windows are small (index-neighbourhood seeds, az_bucket_bound): a warp per query would
-// spend most of its lanes on empty slices there, a thread per query keeps all 32 lanes on real candidates.  Keys are
-// unique ((distance, index) / (distance, visiting order)), so the two front-runners and the third distance do not
-// depend on the visiting order: results are identical to the warp scan by construction.
-__device__ __forceinline__ void az_scan_slice_thread(const AzIndex& ix, const float4 s, int p, int pe, Top3& top) {
-  for (; p < pe; p += 2) {  // two loads in flight
-    const float4 t0 = ld_slot(ix, p), t1 = ld_slot(ix, p + 1 < pe ? p + 1 : p);
+// A GROUP of G lanes per query (G = 4: eight queries per warp): the same scans for small windows.  A warp per query
+// spends most of its lanes on empty slices and its instructions on warp-wide bookkeeping when a window holds a few dozen
+// candidates; with G lanes per query the rings are dealt round-robin to the lanes, every lane keeps its own Top3 and a
+// log2(G)-step butterfly merges them.  Keys are unique ((distance, index) / (distance, visiting order)), so the two
+// front-runners and the third distance of a set of candidates do not depend on who visits what in which order: results
+// are identical to the warp scan by construction.
+template <int G>
+__device__ __forceinline__ void group_top3(Top3& t, unsigned gmask) {
+#pragma unroll
+  for (int m = 1; m < G; m <<= 1) {
+    const unsigned long long ok1 = __shfl_xor_sync(gmask, t.k1, m), ok2 = __shfl_xor_sync(gmask, t.k2, m);
+    const int op1 = __shfl_xor_sync(gmask, t.p1, m), op2 = __shfl_xor_sync(gmask, t.p2, m);
+    const unsigned od3 = __shfl_xor_sync(gmask, t.d3, m);
+    t.insert(ok1, op1);  // (the partner's candidates are disjoint from this lane's; kKeyMax entries change nothing)
+    t.insert(ok2, op2);
+    t.d3 = min(t.d3, od3);
+  }
+}
+// one lane over the slots p, p + step, ... < pe (two loads in flight)
+__device__ __forceinline__ void az_scan_slice_lane(const AzIndex& ix, const float4 s, int p, int pe, int step, Top3& top) {
+  for (; p < pe; p += 2 * step) {
+    const int p1 = p + step;
+    const float4 t0 = ld_slot(ix, p), t1 = ld_slot(ix, p1 < pe ? p1 : p);
     const unsigned d0 = __float_as_uint(sqdist_f32(s.x, s.y, s.z, t0.x, t0.y, t0.z));
     const unsigned d1 = __float_as_uint(sqdist_f32(s.x, s.y, s.z, t1.x, t1.y, t1.z));
     top.insert(((unsigned long long)d0 << 32) | (unsigned)slot_index(t0.w), p);
-    top.insert(p + 1 < pe ? (((unsigned long long)d1 << 32) | (unsigned)slot_index(t1.w)) : kKeyMax, p + 1);
+    top.insert(p1 < pe ? (((unsigned long long)d1 << 32) | (unsigned)slot_index(t1.w)) : kKeyMax, p1);
   }
 }
-__device__ __forceinline__ Top3 az_scan_nn_thread(const AzIndex& ix, const float4 s, int win) {
+template <int G>
+__device__ __forceinline__ Top3 az_scan_nn_group(const AzIndex& ix, const float4 s, int win, int sub, unsigned gmask) {
   const int blo = win >> 16, nbins = win & 0xffff;
   const int e0 = min(blo + nbins, ix.nb), e1 = blo + nbins - ix.nb;
   Top3 top;
   top.init();
-  for (int r = 0; r < ix.nrings; ++r) {
+  for (int r = sub; r < ix.nrings; r += G) {  // rings dealt round-robin to the lanes of the group
     const int base = r * ix.nb;
-    az_scan_slice_thread(ix, s, ix.bstart[base + blo], ix.bstart[base + e0], top);
-    if (e1 > 0) az_scan_slice_thread(ix, s, ix.bstart[base], ix.bstart[base + e1], top);
+    az_scan_slice_lane(ix, s, ix.bstart[base + blo], ix.bstart[base + e0], 1, top);
+    if (e1 > 0) az_scan_slice_lane(ix, s, ix.bstart[base], ix.bstart[base + e1], 1, top);
   }
+  group_top3<G>(top, gmask);
   if ((unsigned)(top.k1 >> 32) >= 0x7f800000u) { top.k1 = kKeyMax; top.p1 = -1; }  // only inf / NaN distances: nothing found
   return top;
 }
@@ -451,41 +468,44 @@ __device__ __forceinline__ WalkOut az_scan_walk(const AzIndex& ix, const float4 
   return o;
 }
 
-// the same walks by ONE thread (see az_scan_nn_thread)
-template <bool SURF>
-__device__ __forceinline__ WalkOut az_scan_walk_thread(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
-                                                       float B2, float B3) {
+// the same walks by a group of G lanes (see az_scan_nn_group): the four adjacent rings are dealt to the lanes, the
+// closest point's own ring (a handful of candidates) is strided over them
+template <bool SURF, int G>
+__device__ __forceinline__ WalkOut az_scan_walk_group(const AzIndex& ix, const float4 s, int ccr, int w2, int w3, int fwdBound, float nearf,
+                                                      float B2, float B3, int sub, unsigned gmask) {
   const int c = ccr & 0x00ffffff, cr = (int)((unsigned)ccr >> 24);
   Top3 t2, t3;
   t2.init(); t3.init();
-#pragma unroll
-  for (int dr = -2; dr <= 2; ++dr) {
-    const int r = cr + dr;
-    const bool cls2 = SURF ? (dr == 0) : true;
-    if (r < 0 || r >= ix.nrings || (!SURF && dr == 0)) continue;
-    const int win = cls2 ? w2 : w3;
+  auto scan_ring = [&](int r, int win, Top3& top, int start, int step) {
     const int blo = win >> 16, nbins = win & 0xffff, base = r * ix.nb;
     for (int seg = 0; seg < 2; ++seg) {
       int p, pe;
       if (seg == 0) { p = ix.bstart[base + blo]; pe = ix.bstart[base + min(blo + nbins, ix.nb)]; }
       else { const int e1 = blo + nbins - ix.nb; if (e1 <= 0) break; p = ix.bstart[base]; pe = ix.bstart[base + e1]; }
-      for (; p < pe; p += 2) {
+      for (p += start; p < pe; p += 2 * step) {
         float4 tt[2];
-        tt[0] = ld_slot(ix, p); tt[1] = ld_slot(ix, p + 1 < pe ? p + 1 : p);
+        tt[0] = ld_slot(ix, p); tt[1] = ld_slot(ix, p + step < pe ? p + step : p);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int pu = p + u;
+          const int pu = p + u * step;
           const float4 t = tt[u];
           const unsigned d = __float_as_uint(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z));
           const int j = slot_index(t.w);
           const bool fwd = j > c;
           const bool adm = pu < pe && j != c && (!fwd || j < fwdBound);
-          const unsigned long long k = adm ? (((unsigned long long)d << 32) | (fwd ? order_fwd(j) : order_bwd(j))) : kKeyMax;
-          if (cls2) t2.insert(k, pu); else t3.insert(k, pu);
+          top.insert(adm ? (((unsigned long long)d << 32) | (fwd ? order_fwd(j) : order_bwd(j))) : kKeyMax, pu);
         }
       }
     }
+  };
+  if (SURF && cr < ix.nrings) scan_ring(cr, w2, t2, sub, G);
+  for (int idx = sub; idx < 4; idx += G) {
+    const int r = cr + (idx < 2 ? idx - 2 : idx - 1);
+    if (r < 0 || r >= ix.nrings) continue;
+    if (SURF) scan_ring(r, w3, t3, 0, 1); else scan_ring(r, w2, t2, 0, 1);
   }
+  group_top3<G>(t2, gmask);
+  if (SURF) group_top3<G>(t3, gmask);
   const float gate = sqrtf(nearf);
   const unsigned nearbits = __float_as_uint(nearf);
   WalkOut o;

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lins_ieskf_kernel(const __
   if (tid == 0) {
     mbar_init(&cta.mbar, 1);
     cta.phase = 0;
-    cta.wl_n[0] = 0; cta.wl_n[1] = 0; cta.wl_tn[0] = 0; cta.wl_tn[1] = 0; cta.wl_head[0] = 0; cta.wl_head[1] = 0; cta.dbg[0] = 0; cta.dbg[1] = 0;  // (reset after every pass)
+    cta.wl_n[0] = 0; cta.wl_n[1] = 0; cta.wl_tn[0] = 0; cta.wl_tn[1] = 0; cta.wl_thead[0] = 0; cta.wl_thead[1] = 0; cta.wl_head[0] = 0; cta.wl_head[1] = 0; cta.dbg[0] = 0; cta.dbg[1] = 0;  // (reset after every pass)
     cta.exhausted = 0; cta.any_finished = 0;
     for (int s = 0; s < S; ++s) { slots[s].scan = -1; slots[s].fresh = 0; slots[s].run = 0; slots[s].finished = 0; }
     fence_mbar_init();
@@ -945,11 +945,22 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
   // Clouds in caller-PINNED host memory (cudaHostAlloc / cudaHostRegister): the copy engine reads the raw 32-B records
   // straight from the caller's buffer and a device kernel packs them — no host pass over the points at all (twice the
   // PCIe bytes, zero host memory traffic besides the DMA reads; what makes a many-GPU host scale).  LINS_UPLOAD=pack
-  // forces the host-pack path, LINS_UPLOAD=pinned fails the call when a cloud is not pinned.
+  // forces the host-pack path, LINS_UPLOAD=direct the DMA path for every pinned cloud, LINS_UPLOAD=pinned additionally
+  // fails the call when a cloud is not pinned.
   bool direct[4] = {false, false, false, false};
+  // pack threads: LINS_PACK_THREADS when set (a job that runs several contexts / ranks per host divides the cores
+  // among them), else half the hardware threads, at most 32
+  int want_threads;
   {
+    unsigned hw = std::thread::hardware_concurrency();
+    want_threads = (int)std::min<unsigned>(hw ? hw / 2 : 4, 32);
+    if (const char* e = std::getenv("LINS_PACK_THREADS")) { const int v = std::atoi(e); if (v >= 1) want_threads = std::min(v, 64); }
+  }
+  {
+    // default policy: with plenty of host threads per context the host pack wins (half the PCIe bytes); with few — many
+    // contexts / ranks sharing one host — the raw DMA does (no host memory traffic beyond the DMA reads)
     const char* mode = std::getenv("LINS_UPLOAD");
-    const bool force_pack = mode && std::strcmp(mode, "pack") == 0;
+    const bool force_pack = (mode && std::strcmp(mode, "pack") == 0) || (!mode && want_threads >= 8);
     for (int k = 0; k < 4 && !force_pack; ++k) {
       if (seg[k + 1] == seg[k]) continue;
       cudaPointerAttributes at;
@@ -992,12 +1003,7 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
         if (e != cudaSuccess) cuda_err.store((int)e);
       }
     };
-    // pack threads: LINS_PACK_THREADS when set (a job that runs several contexts / ranks per host divides the cores
-    // among them), else half the hardware threads, at most 32
-    unsigned hw = std::thread::hardware_concurrency();
-    int want = (int)std::min<unsigned>(hw ? hw / 2 : 4, 32);
-    if (const char* e = std::getenv("LINS_PACK_THREADS")) { const int v = std::atoi(e); if (v >= 1) want = std::min(v, 64); }
-    int nthr = (int)std::min<size_t>((size_t)want, std::max<size_t>(slices.size(), 1));
+    int nthr = (int)std::min<size_t>((size_t)want_threads, std::max<size_t>(slices.size(), 1));
     if (nthr < 1) nthr = 1;
     if (!slices.empty()) ctx->pool.run(nthr, worker);
     if (cuda_err.load() != 0) return fail(ctx, LINS_E_CUDA, "H2D copy of a packed slice", (cudaError_t)cuda_err.load());

@@ -143,7 +143,7 @@ struct CtaMem {
   } u;
   int scan_tmp[kThreads];
   int wl_n[2], wl_head[2];  // work lists of the closest-point / walk phases (entries, next entry to hand out)
-  int wl_tn[2];             // ... and their thread-level lists (filled from the back of the same array)
+  int wl_tn[2], wl_thead[2];  // ... and their group-level lists (filled from the back of the same array)
   int dbg[2];               // diagnostics (only touched when phase timers are enabled)
   int n_active, any_fresh, any_finished, any_legacy, any_indexed, exhausted, pass_first;
   unsigned long long mbar;
