@@ -151,6 +151,13 @@ int lins_gpu_estimate_transform(lins_ctx* ctx, const lins_point* surf_flat, int 
 int lins_gpu_update_map(lins_ctx* ctx, lins_point* surf_less_flat, int n_surf, lins_point* corner_less_sharp,
                         int n_corner, const double* lin_state, int* map_replaced);
 
+/* The same with the device-resident options: lin_state == NULL uses the posterior the last lins_gpu_ieskf left on the
+   device; surf_out / corner_out receive the transformed clouds (may alias the inputs; NULL = keep them on the device only:
+   no D2H, no stream synchronisation — the call returns with the refresh queued).  *map_replaced as above. */
+int lins_gpu_update_map_ex(lins_ctx* ctx, const lins_point* surf_less_flat, int n_surf, const lins_point* corner_less_sharp,
+                           int n_corner, const double* lin_state, lins_point* surf_out, lins_point* corner_out,
+                           int* map_replaced);
+
 /* Batched mode. upload: pack + H2D, resident afterwards. run: launch the fused kernel over the resident
    batch on the ctx stream (asynchronous). download: D2H of results + stream sync; any pointer may be NULL. */
 int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* batch);

@@ -28,24 +28,34 @@ EXPORTS = [
     "lins_gpu_batch_upload", "lins_gpu_batch_run", "lins_gpu_batch_download", "lins_gpu_ieskf_batch",
     "lins_gpu_batch_results_device", "lins_gpu_batch_jacobian_pass", "lins_gpu_launch_count", "lins_gpu_sync",
     "lins_gpu_debug_phase_cycles", "lins_gpu_map_set", "lins_gpu_scan2map", "lins_gpu_map_associate",
-    "lins_gpu_host_register", "lins_gpu_host_unregister", "lins_gpu_batch_download_indices",
+    "lins_gpu_host_register", "lins_gpu_host_unregister", "lins_gpu_batch_download_indices", "lins_gpu_update_map_ex",
 ]
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+NVCC_COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+# translation units and their extra flags: lins_gpu.cu (C-ABI + the fused kernel: bit-exact association, no multiply-add
+# contraction), lins_jacobian.cu (the tolerance-checked split Jacobian kernel: contraction allowed)
+UNITS = [("lins_gpu.cu", ["-fmad=false"]), ("lins_jacobian.cu", [])]
+NVCC_FLAGS = NVCC_COMMON + ["-fmad=false", "-shared"]  # (what tools/ scripts print)
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/cuda/lins_gpu.cu -> liblins_gpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    main = os.path.join(CUDA_DIR, "lins_gpu.cu")
-    deps = [main, os.path.join(_ROOT, "include", "lins_gpu.h")]
-    for d in (CUDA_DIR, os.path.join(os.path.dirname(CUDA_DIR), "host")):  # every header the translation unit includes
+def build(force=False, verbose=False, out=None, extra=()):
+    """Compile csrc/cuda/*.cu -> liblins_gpu.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = out or LIB_PATH
+    deps = [os.path.join(CUDA_DIR, u) for u, _ in UNITS] + [os.path.join(_ROOT, "include", "lins_gpu.h")]
+    for d in (CUDA_DIR, os.path.join(os.path.dirname(CUDA_DIR), "host")):  # every header the translation units include
         deps += [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cuh", ".hpp", ".h"))]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in deps):
-        return LIB_PATH
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, main]
-    subprocess.check_call(cmd)
-    return LIB_PATH
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in deps):
+        return out
+    objdir = os.path.join(_PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    tag = os.path.splitext(os.path.basename(out))[0]
+    objs = []
+    for unit, flags in UNITS:
+        obj = os.path.join(objdir, f"{tag}_{os.path.splitext(unit)[0]}.o")
+        subprocess.check_call(["nvcc"] + NVCC_COMMON + flags + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CUDA_DIR, unit)])
+        objs.append(obj)
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs)
+    return out
 
 
 _LIB = None
@@ -69,6 +79,8 @@ def lib():
         L.lins_gpu_associate.argtypes = [vp, vp, C.c_int, vp, C.c_int, f64p, C.c_int, i32p, i32p, f32p, f32p, u8p, u8p, f32p, f32p]
         L.lins_gpu_estimate_transform.argtypes = [vp, vp, C.c_int, vp, C.c_int, f64p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.lins_gpu_update_map.argtypes = [vp, vp, C.c_int, vp, C.c_int, f64p, C.POINTER(C.c_int)]
+        if hasattr(L, "lins_gpu_update_map_ex"):  # (absent from older A/B variant libraries selected through LINS_GPU_LIB)
+            L.lins_gpu_update_map_ex.argtypes = [vp, vp, C.c_int, vp, C.c_int, f64p, vp, vp, C.POINTER(C.c_int)]
         L.lins_gpu_batch_upload.argtypes = [vp, C.POINTER(LinsBatchDesc)]
         L.lins_gpu_batch_run.argtypes = [vp]
         L.lins_gpu_batch_download.argtypes = [vp, f64p, f64p, vp, vp]
@@ -209,6 +221,15 @@ class LinsGpu:
         rep = C.c_int(0)
         self._ck(self.L.lins_gpu_update_map(self.h, ptr(s), len(s), ptr(c), len(c), ptr(st), C.byref(rep)))
         return s, c, bool(rep.value)
+
+    def update_map_device(self, surf_less_flat, corner_less_sharp, lin_state=None):
+        """Map refresh that stays on the device: no read-back, no synchronisation; lin_state None = the posterior of the
+        last ieskf() call, still resident."""
+        s, c = as_points(surf_less_flat), as_points(corner_less_sharp)
+        st = None if lin_state is None else np.ascontiguousarray(lin_state, dtype=np.float64).reshape(STATE_DIM)
+        rep = C.c_int(0)
+        self._ck(self.L.lins_gpu_update_map_ex(self.h, ptr(s), len(s), ptr(c), len(c), ptr(st), None, None, C.byref(rep)))
+        return bool(rep.value)
 
     # ---- row F2: scan-to-map refinement of the mapping node ---------------------------------------------------------
     def map_set(self, corner_from_map, surf_from_map):

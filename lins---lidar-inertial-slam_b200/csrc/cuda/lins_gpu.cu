@@ -25,9 +25,13 @@
 #include "../host/host_pool.hpp"
 #include "../host/lins_map_host.hpp"
 #include "lins_assoc.cuh"
+#include "lins_icp_step.cuh"
 #include "lins_map.cuh"
 
 using namespace lins_dev;
+
+// lins_jacobian.cu
+extern "C" int lins_launch_jacobian_mma(const lins_dev::BatchView* bv, const lins_dev::KParams* kp, int n_units, int sm_count, cudaStream_t stream);
 
 namespace {
 
@@ -272,6 +276,7 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lins_ieskf_kernel(const __
   const int tid = threadIdx.x, warp = tid >> 5;
   const double sig2 = kp.lidar_std * kp.lidar_std;
   (void)slot_at;
+  if (MODE == MODE_ICP_REDUCE && bv.icp_done && *bv.icp_done) return;  // the queued tail of a converged ICP loop (uniform)
 
   if (tid == 0) {
     mbar_init(&cta.mbar, 1);
@@ -364,7 +369,8 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) lins_ieskf_kernel(const __
 }
 
 
-// Split "Jacobian kernel" (SURVEY.md §8(d) unit U1; rows A5-A9 form B given the correspondence IDs).
+// Split "Jacobian kernel", shuffle-fold version (kept for A/B runs, LINS_JAC_VARIANT=2; the default is the tensor-core fold
+// of lins_jacobian.cu).  SURVEY.md §8(d) unit U1; rows A5-A9 form B given the correspondence IDs.
 // One warp per scan: streams the scan's queries (16 B each, coalesced) and IDs (12 / 8 B, coalesced), gathers
 // the 3 / 2 matched targets (16 B each), recomputes de-skew, residual, weight and Jacobian row.  Every trip of 32
 // queries is folded across the warp straight away (warp_fold_row: lane e owns sum e), so a lane carries ONE running
@@ -445,7 +451,7 @@ __global__ void __launch_bounds__(kJacThreads, kJacMinBlocks) lins_jacobian_kern
 
 // F1: transformToEnd (StateEstimator.hpp:1083-1101) of a packed cloud, in place on device.
 __global__ void lins_transform_to_end_kernel(float4* __restrict__ pts, int n, const double* __restrict__ lin,
-                                             double scan_period) {
+                                             double scan_period, lins_point* __restrict__ out32) {
   __shared__ double sphi[3], srn[3], sq[4];
   if (threadIdx.x == 0) {
     q4 q; q.x = lin[6]; q.y = lin[7]; q.z = lin[8]; q.w = lin[9];
@@ -466,6 +472,11 @@ __global__ void lins_transform_to_end_kernel(float4* __restrict__ pts, int n, co
   d3 P2 = qrot(qinverse(q), sub3(P1, mk3(srn[0], srn[1], srn[2])));
   p.x = (float)P2.x; p.y = (float)P2.y; p.z = (float)P2.z;
   pts[i] = p;
+  if (out32) {  // full pcl::PointXYZI records for a straight D2H into the caller's cloud
+    float4* o = reinterpret_cast<float4*>(out32 + i);
+    o[0] = make_float4(p.x, p.y, p.z, 1.0f);
+    o[1] = make_float4(p.w, 0.f, 0.f, 0.f);
+  }
 }
 
 // pcl::PointXYZI records (32 B) -> packed (x, y, z, intensity) (16 B) on the device: the upload path of clouds that
@@ -522,6 +533,8 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   int max_ts = 0, max_tc = 0;
   DevBuf<int> qs_off, qc_off, ts_off, tc_off, ind_s, ind_c, counter;
   DevBuf<long long> timers;
+  DevBuf<IcpState> icp;            // pose-update state of the ICP fallback loop (lins_gpu_estimate_transform)
+  PinBuf<IcpState> h_icp;
   DevBuf<double> state_in, cov_in, state_out, cov_out, accum;
   DevBuf<lins_scan_result> results;
   DevBuf<lins_report> reports;
@@ -538,7 +551,7 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
     state_out.release(); cov_out.release(); accum.release(); results.release(); reports.release(); sel_s.release();
     sel_c.release(); coeff_s.release(); coeff_c.release(); mask_s.release(); mask_c.release(); h_pts.release();
     h_off.release(); h_state.release(); h_cov.release(); h_state_out.release(); h_cov_out.release();
-    h_accum.release(); h_results.release(); h_reports.release();
+    h_accum.release(); h_results.release(); h_reports.release(); icp.release(); h_icp.release();
   }
 };
 
@@ -565,6 +578,8 @@ struct lins_ctx {
   bool verbose = false;  // LINS_VERBOSE: print the launch configuration
   int force_slots = 0;  // tuning knob (LINS_SLOTS): resident units per CTA
   DevBuf<float4> tmp_pts;
+  DevBuf<lins_point> tmp_out;  // transformed clouds as full PointXYZI records (update_map read-back)
+  cudaEvent_t tmp_ev = nullptr; // recorded after the last H2D copies that read h_tmp
   DevBuf<double> tmp_lin;
   PinBuf<float4> h_tmp;
   // row F2 (scan-to-map refinement): the map clouds, the current feature clouds, search / reduction scratch
@@ -771,11 +786,22 @@ BatchView single_view(lins_ctx* ctx, bool trace) {
   return bv;
 }
 
+// ctx->h_tmp is pinned staging that asynchronous H2D copies read: before it is rewritten, wait for the event recorded
+// after the last copies that read it (already complete in steady state: no stream synchronisation)
+cudaError_t tmp_staging_wait(lins_ctx* ctx) {
+  if (!ctx->tmp_ev) return cudaSuccess;
+  return cudaEventSynchronize(ctx->tmp_ev);
+}
+cudaError_t tmp_staging_mark(lins_ctx* ctx) {
+  if (!ctx->tmp_ev) { cudaError_t e = cudaEventCreateWithFlags(&ctx->tmp_ev, cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+  return cudaEventRecord(ctx->tmp_ev, ctx->stream);
+}
+
 int upload_map_offsets(lins_ctx* ctx) {
   CK(ctx->map_off.reserve(8));
   int h[8] = {0, ctx->map_ns, 0, ctx->map_nc, 0, ctx->tree_ns, 0, ctx->tree_nc};
+  // (h is pageable stack memory: cudaMemcpyAsync returns once it has been copied to the driver's staging buffer)
   CK(cudaMemcpyAsync(ctx->map_off.p, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));  // h is on the stack
   return LINS_OK;
 }
 
@@ -821,7 +847,8 @@ void lins_gpu_destroy(lins_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ctx->batch.release(); ctx->single.release();
   ctx->map_s.release(); ctx->map_c.release(); ctx->tree_s.release(); ctx->tree_c.release(); ctx->map_off.release();
-  ctx->tmp_pts.release(); ctx->tmp_lin.release(); ctx->h_tmp.release(); ctx->mp.release();
+  ctx->tmp_pts.release(); ctx->tmp_lin.release(); ctx->tmp_out.release(); ctx->h_tmp.release(); ctx->mp.release();
+  if (ctx->tmp_ev) cudaEventDestroy(ctx->tmp_ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -842,11 +869,13 @@ int lins_gpu_set_map(lins_ctx* ctx, const lins_point* surf, int ns, const lins_p
   if (ns < 0 || nc < 0 || (ns > 0 && !surf) || (nc > 0 && !corner)) return fail(ctx, LINS_E_INVALID, "bad map cloud");
   CK(cudaSetDevice(ctx->device));
   CK(ctx->map_s.reserve(ns + 1)); CK(ctx->map_c.reserve(nc + 1));
+  CK(tmp_staging_wait(ctx));
   CK(ctx->h_tmp.reserve((size_t)ns + nc + 1));
   pack_into(ctx->h_tmp.p, surf, ns);
   pack_into(ctx->h_tmp.p + ns, corner, nc);
   if (ns) CK(cudaMemcpyAsync(ctx->map_s.p, ctx->h_tmp.p, sizeof(float4) * ns, cudaMemcpyHostToDevice, ctx->stream));
   if (nc) CK(cudaMemcpyAsync(ctx->map_c.p, ctx->h_tmp.p + ns, sizeof(float4) * nc, cudaMemcpyHostToDevice, ctx->stream));
+  CK(tmp_staging_mark(ctx));
   ctx->map_ns = ns; ctx->map_nc = nc; ctx->tree_ns = ns; ctx->tree_nc = nc; ctx->tree_is_map = true;
   return upload_map_offsets(ctx);
 }
@@ -1277,20 +1306,17 @@ int lins_gpu_batch_jacobian_pass(lins_ctx* ctx, double* accum_out) {
   BatchView bv = view_of(r, false, false);
   bv.state_in = r.state_out.p;  // linearise at the updated state; IDs = the last iteration's
   KParams kp = make_kparams(ctx->prm, MODE_JACOBIAN, 1);
-  // one warp per scan; the occupancy / register trade-off is a launch-bounds choice (LINS_JAC_VARIANT: tuning knob)
+  // default: lins_jacobian.cu (FP64 tensor-core fold, multiply-add contraction); LINS_JAC_VARIANT=2: the shuffle-fold
+  // kernel above (this TU, -fmad=false)
   static const int variant = [] { const char* e = std::getenv("LINS_JAC_VARIANT"); return e ? std::atoi(e) : 0; }();
-  auto go = [&](auto kernel, int threads, int min_blocks) {
-    const int wpb = threads / 32;
-    int grid = std::min((r.n + wpb - 1) / wpb, ctx->sm_count * min_blocks);
+  if (variant == 2) {
+    const int wpb = 128 / 32;
+    int grid = std::min((r.n + wpb - 1) / wpb, ctx->sm_count * 5);
     if (grid < 1) grid = 1;
-    kernel<<<grid, threads, 0, ctx->stream>>>(bv, kp);
-  };
-  switch (variant) {
-    // measured on B200, 5000 scans (408 MB working set): <256,1> 148 us, <128,4> 101 us, <128,5> 94 us, <128,6> 100 us
-    case 1: go(lins_jacobian_kernel<128, 4>, 128, 4); break;
-    case 3: go(lins_jacobian_kernel<128, 6>, 128, 6); break;
-    case 4: go(lins_jacobian_kernel<256, 1>, 256, 8); break;  // round-1 first version: 156 registers, one CTA resident per SM
-    default: go(lins_jacobian_kernel<128, 5>, 128, 5); break;  // 96 registers (324 B of spills), 20 warps per SM
+    lins_jacobian_kernel<128, 5><<<grid, 128, 0, ctx->stream>>>(bv, kp);  // measured: 83 us per 5000 units (96 registers, 20 warps per SM)
+  } else {
+    const int e = lins_launch_jacobian_mma(&bv, &kp, r.n, ctx->sm_count, ctx->stream);
+    if (e != 0) return fail(ctx, LINS_E_CUDA, "jacobian kernel launch", (cudaError_t)e);
   }
   CK(cudaGetLastError());
   ctx->launches += 1;
@@ -1303,10 +1329,8 @@ int lins_gpu_batch_jacobian_pass(lins_ctx* ctx, double* accum_out) {
   return LINS_OK;
 }
 
-// ≙ estimateTransform (StateEstimator.hpp:1163-1196): the association + J^T J / J^T b reduction of every
-// Gauss-Newton step runs on device (MODE_ICP_REDUCE); the 6x6 solve / degeneracy projection / pose update of
-// calculateTransformation (:1260-1320) run on the host (rare fallback path: one small D2H per step).
-int lins_gpu_estimate_transform(lins_ctx* ctx, const lins_point* surf_flat, int ns, const lins_point* corner_sharp,
+// (A/B only, LINS_ICP_HOST_LOOP=1: the round-1 flow — one reduction launch, D2H and host 6x6 step per iteration)
+static int estimate_transform_host_loop(lins_ctx* ctx, const lins_point* surf_flat, int ns, const lins_point* corner_sharp,
                                 int nc, double* pose_io, int* iters_out, int* converged_out) {
   if (!ctx) return LINS_E_INVALID;
   if (!pose_io) return fail(ctx, LINS_E_INVALID, "null pose");
@@ -1342,11 +1366,13 @@ int lins_gpu_estimate_transform(lins_ctx* ctx, const lins_point* surf_flat, int 
     for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { JTJ[i][j] = a[k]; JTJ[j][i] = a[k]; ++k; }
     for (int i = 0; i < 6; ++i) JTb[i] = a[21 + i];
     linalg::Vec<6> x = linalg::colPivQrSolve<6>(JTJ, JTb);
+    if (ctx->verbose) std::fprintf(stderr, "[lins_gpu] icp iter %d x (before projection): %.12g %.12g %.12g %.12g %.12g %.12g\n", iter, x[0], x[1], x[2], x[3], x[4], x[5]);
     bool isDegenerate = false;
     if (iter == 0) {  // :1269-1296
       linalg::Vec<6> matE;
       linalg::Mat<6> matV, matV2, Vinv;
       linalg::symmetricEigen<6>(JTJ, matE, matV);
+      if (ctx->verbose) std::fprintf(stderr, "[lins_gpu] icp E: %.9g %.9g %.9g %.9g %.9g %.9g\n", matE[0], matE[1], matE[2], matE[3], matE[4], matE[5]);
       matV2 = matV;
       for (int i = 0; i < 6; ++i) {
         if (matE[i] < 10.) { for (int j = 0; j < 6; ++j) matV2[i][j] = 0; isDegenerate = true; }
@@ -1355,6 +1381,7 @@ int lins_gpu_estimate_transform(lins_ctx* ctx, const lins_point* surf_flat, int 
       if (!linalg::inverse<6>(matV, Vinv)) for (auto& row : Vinv) for (auto& e : row) e = std::numeric_limits<double>::quiet_NaN();
       for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) { double sacc = 0; for (int m = 0; m < 6; ++m) sacc += Vinv[i][m] * matV2[m][j]; matP[i][j] = sacc; }
     }
+    if (ctx->verbose) std::fprintf(stderr, "[lins_gpu] icp iter %d degenerate %d\n", iter, (int)isDegenerate);
     if (isDegenerate) {
       linalg::Vec<6> x2 = x;
       for (int i = 0; i < 6; ++i) { double sacc = 0; for (int j = 0; j < 6; ++j) sacc += matP[i][j] * x2[j]; x[i] = sacc; }
@@ -1373,45 +1400,113 @@ int lins_gpu_estimate_transform(lins_ctx* ctx, const lins_point* surf_flat, int 
   return LINS_OK;
 }
 
-// ≙ updatePointCloud (StateEstimator.hpp:1116-1161), XYZ part: transformToEnd on device, results copied back
-// into the caller's clouds (the reference transforms scan_new_'s clouds in place), then the map swap + the
-// guarded index refresh.
-int lins_gpu_update_map(lins_ctx* ctx, lins_point* surf, int ns, lins_point* corner, int nc, const double* lin_state,
-                        int* map_replaced) {
+// ≙ estimateTransform (StateEstimator.hpp:1163-1196): the association + J^T J / J^T b reduction of every
+// Gauss-Newton step runs on device (MODE_ICP_REDUCE), and so do the 6x6 solve / degeneracy projection / pose update of
+// calculateTransformation (:1260-1320): lins_icp_step.cuh.
+int lins_gpu_estimate_transform(lins_ctx* ctx, const lins_point* surf_flat, int ns, const lins_point* corner_sharp,
+                                int nc, double* pose_io, int* iters_out, int* converged_out) {
   if (!ctx) return LINS_E_INVALID;
-  if (ns < 0 || nc < 0 || (ns > 0 && !surf) || (nc > 0 && !corner) || !lin_state) return fail(ctx, LINS_E_INVALID, "bad update_map args");
+  if (!pose_io) return fail(ctx, LINS_E_INVALID, "null pose");
   CK(cudaSetDevice(ctx->device));
+  if (std::getenv("LINS_ICP_HOST_LOOP")) return estimate_transform_host_loop(ctx, surf_flat, ns, corner_sharp, nc, pose_io, iters_out, converged_out);
+  // queries + initial pose are staged ONCE; every Gauss-Newton iteration is a reduction launch (MODE_ICP_REDUCE, linearised
+  // at the pose block on the device) + the one-thread step kernel that updates that block; once the step kernel sets
+  // `done` the remaining queued launches return immediately.  One D2H + one synchronisation at the end.
+  double lin[19];
+  std::memset(lin, 0, sizeof(lin));
+  lin[0] = pose_io[0]; lin[1] = pose_io[1]; lin[2] = pose_io[2];
+  lin[6] = pose_io[3]; lin[7] = pose_io[4]; lin[8] = pose_io[5]; lin[9] = pose_io[6];
+  int rc = stage_single(ctx, surf_flat, ns, corner_sharp, nc, lin, nullptr, false);
+  if (rc != LINS_OK) return rc;
+  Resident& r = ctx->single;
+  CK(r.icp.reserve(1)); CK(r.h_icp.reserve(1)); CK(r.h_state_out.reserve(20));
+  CK(cudaMemsetAsync(r.icp.p, 0, sizeof(IcpState), ctx->stream));
+  for (int iter = 0; iter < ctx->prm.num_iter; ++iter) {
+    BatchView bv = single_view(ctx, false);
+    bv.icp_done = &r.icp.p->done;
+    rc = launch(ctx, r, bv, make_kparams(ctx->prm, MODE_ICP_REDUCE, iter));
+    if (rc != LINS_OK) return rc;
+    lins_icp_step_kernel<<<1, 32, 0, ctx->stream>>>(r.accum.p, r.state_in.p, r.icp.p, iter);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  CK(cudaMemcpyAsync(r.h_state_out.p, r.state_in.p, sizeof(double) * 20, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(r.h_icp.p, r.icp.p, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const double* so = r.h_state_out.p;
+  pose_io[0] = so[0]; pose_io[1] = so[1]; pose_io[2] = so[2];
+  pose_io[3] = so[6]; pose_io[4] = so[7]; pose_io[5] = so[8]; pose_io[6] = so[9];
+  if (iters_out) *iters_out = r.h_icp.p->iters;
+  if (converged_out) *converged_out = r.h_icp.p->converged;
+  return LINS_OK;
+}
+
+// ≙ updatePointCloud (StateEstimator.hpp:1116-1161), XYZ part: transformToEnd on the device, then the map swap + the
+// guarded index refresh.  The clouds stay on the device as the next map; copying them back is optional (the reference
+// transforms scan_new_'s clouds in place because the mapping node consumes them) and, when asked for, is one D2H of
+// full PointXYZI records straight into the caller's clouds — one stream synchronisation per call, none without read-back.
+int lins_gpu_update_map_ex(lins_ctx* ctx, const lins_point* surf, int ns, const lins_point* corner, int nc, const double* lin_state,
+                           lins_point* surf_out, lins_point* corner_out, int* map_replaced) {
+  if (!ctx) return LINS_E_INVALID;
+  if (ns < 0 || nc < 0 || (ns > 0 && !surf) || (nc > 0 && !corner)) return fail(ctx, LINS_E_INVALID, "bad update_map args");
+  CK(cudaSetDevice(ctx->device));
+  const double* lin_dev = nullptr;
+  if (!lin_state) {  // the posterior the last lins_gpu_ieskf left on the device (linState_ of a run that did not diverge)
+    if (ctx->single.n != 1 || !ctx->single.state_out.p) return fail(ctx, LINS_E_INVALID, "no device-resident state: call lins_gpu_ieskf first or pass lin_state");
+    lin_dev = ctx->single.state_out.p;
+  }
   const bool rebuild = nc >= 5 && ns >= 20;  // :1156-1157
-  // keep the old map alive as the 1-NN cloud if the guard fails
-  if (!rebuild && ctx->tree_is_map) {
+  const bool want_out = (ns > 0 && surf_out) || (nc > 0 && corner_out);
+  // every allocation first: the context is only changed once nothing can fail any more
+  const bool keep_tree = !rebuild && ctx->tree_is_map;  // keep the old map alive as the 1-NN cloud if the guard fails
+  DevBuf<float4>& dst_s = keep_tree ? ctx->tree_s : ctx->map_s;  // (after the swap below these are the new map buffers)
+  DevBuf<float4>& dst_c = keep_tree ? ctx->tree_c : ctx->map_c;
+  CK(dst_s.reserve(ns + 1)); CK(dst_c.reserve(nc + 1));
+  CK(ctx->map_s.reserve(1)); CK(ctx->map_c.reserve(1)); CK(ctx->tree_s.reserve(1)); CK(ctx->tree_c.reserve(1));
+  CK(tmp_staging_wait(ctx));  // (the H2D of a previous call may still be reading the pinned staging)
+  CK(ctx->h_tmp.reserve((size_t)ns + nc + 1));
+  CK(ctx->tmp_lin.reserve(20));
+  if (want_out) CK(ctx->tmp_out.reserve((size_t)ns + nc + 1));
+  if (keep_tree) {
     std::swap(ctx->tree_s, ctx->map_s); std::swap(ctx->tree_c, ctx->map_c);
     ctx->tree_ns = std::max(ctx->map_ns, 0); ctx->tree_nc = std::max(ctx->map_nc, 0);
     ctx->tree_is_map = false;
   }
-  CK(ctx->map_s.reserve(ns + 1)); CK(ctx->map_c.reserve(nc + 1));
-  CK(ctx->tree_s.reserve(1)); CK(ctx->tree_c.reserve(1));
-  CK(ctx->h_tmp.reserve((size_t)ns + nc + 1));
-  CK(ctx->tmp_lin.reserve(20));
   pack_into(ctx->h_tmp.p, surf, ns);
   pack_into(ctx->h_tmp.p + ns, corner, nc);
-  double lin[20];
-  std::memcpy(lin, lin_state, sizeof(double) * 19);
-  lin[19] = 0;
-  CK(cudaMemcpyAsync(ctx->tmp_lin.p, lin, sizeof(lin), cudaMemcpyHostToDevice, ctx->stream));
+  if (lin_state) {
+    double lin[20];
+    std::memcpy(lin, lin_state, sizeof(double) * 19);
+    lin[19] = 0;
+    CK(cudaMemcpyAsync(ctx->tmp_lin.p, lin, sizeof(lin), cudaMemcpyHostToDevice, ctx->stream));  // (pageable source: staged before the call returns)
+    lin_dev = ctx->tmp_lin.p;
+  }
   if (ns) CK(cudaMemcpyAsync(ctx->map_s.p, ctx->h_tmp.p, sizeof(float4) * ns, cudaMemcpyHostToDevice, ctx->stream));
   if (nc) CK(cudaMemcpyAsync(ctx->map_c.p, ctx->h_tmp.p + ns, sizeof(float4) * nc, cudaMemcpyHostToDevice, ctx->stream));
-  if (ns) { lins_transform_to_end_kernel<<<(ns + 255) / 256, 256, 0, ctx->stream>>>(ctx->map_s.p, ns, ctx->tmp_lin.p, ctx->prm.scan_period); ctx->launches += 1; }
-  if (nc) { lins_transform_to_end_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(ctx->map_c.p, nc, ctx->tmp_lin.p, ctx->prm.scan_period); ctx->launches += 1; }
+  CK(tmp_staging_mark(ctx));
+  lins_point* o_s = surf_out && ns ? ctx->tmp_out.p : nullptr;
+  lins_point* o_c = corner_out && nc ? ctx->tmp_out.p + ns : nullptr;
+  if (ns) { lins_transform_to_end_kernel<<<(ns + 255) / 256, 256, 0, ctx->stream>>>(ctx->map_s.p, ns, lin_dev, ctx->prm.scan_period, o_s); ctx->launches += 1; }
+  if (nc) { lins_transform_to_end_kernel<<<(nc + 255) / 256, 256, 0, ctx->stream>>>(ctx->map_c.p, nc, lin_dev, ctx->prm.scan_period, o_c); ctx->launches += 1; }
   CK(cudaGetLastError());
-  if (ns) CK(cudaMemcpyAsync(ctx->h_tmp.p, ctx->map_s.p, sizeof(float4) * ns, cudaMemcpyDeviceToHost, ctx->stream));
-  if (nc) CK(cudaMemcpyAsync(ctx->h_tmp.p + ns, ctx->map_c.p, sizeof(float4) * nc, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < ns; ++i) { surf[i].x = ctx->h_tmp.p[i].x; surf[i].y = ctx->h_tmp.p[i].y; surf[i].z = ctx->h_tmp.p[i].z; }
-  for (int i = 0; i < nc; ++i) { corner[i].x = ctx->h_tmp.p[ns + i].x; corner[i].y = ctx->h_tmp.p[ns + i].y; corner[i].z = ctx->h_tmp.p[ns + i].z; }
   ctx->map_ns = ns; ctx->map_nc = nc;
   if (rebuild) { ctx->tree_is_map = true; ctx->tree_ns = ns; ctx->tree_nc = nc; }
   if (map_replaced) *map_replaced = rebuild ? 1 : 0;
-  return upload_map_offsets(ctx);
+  int rc = upload_map_offsets(ctx);
+  if (rc != LINS_OK) return rc;
+  if (want_out) {
+    if (o_s) CK(cudaMemcpyAsync(surf_out, o_s, sizeof(lins_point) * ns, cudaMemcpyDeviceToHost, ctx->stream));
+    if (o_c) CK(cudaMemcpyAsync(corner_out, o_c, sizeof(lins_point) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return LINS_OK;
+}
+
+int lins_gpu_update_map(lins_ctx* ctx, lins_point* surf, int ns, lins_point* corner, int nc, const double* lin_state,
+                        int* map_replaced) {
+  if (!ctx) return LINS_E_INVALID;
+  if (!lin_state) return fail(ctx, LINS_E_INVALID, "bad update_map args");
+  return lins_gpu_update_map_ex(ctx, surf, ns, corner, nc, lin_state, surf, corner, map_replaced);
 }
 
 }  // extern "C"

@@ -72,6 +72,7 @@ struct BatchView {
   long long* timers;                     // optional: per-phase SM cycles summed over CTAs (diagnostics), 64 slots
   int qtile;                             // per-slot capacity of the per-query arrays (>= the largest unit, multiple of 32)
   int nslots;                            // resident units per CTA
+  const int* icp_done;                   // MODE_ICP_REDUCE: non-zero = the Gauss-Newton loop has converged, return at once (or null)
   unsigned char* qscratch;               // per-CTA global scratch for the per-query arrays when they do not fit shared
   size_t qscratch_stride;                // memory (null: they live in shared memory)
 };
@@ -178,7 +179,7 @@ __device__ __forceinline__ float4 transform_to_start(const float4 p, const Smem&
 
 // Is the cloud ring-sorted with every ring in [0, kMaxRing)?  (what the reference's extractFeatures emits, :727-826; the
 // (ring, azimuth) index requires it).  Block-wide; *sorted_flag is valid after the trailing barrier.
-__device__ void check_ring_sorted(const float4* __restrict__ tgt, int T, int* sorted_flag) {
+__device__ inline void check_ring_sorted(const float4* __restrict__ tgt, int T, int* sorted_flag) {
   if (threadIdx.x == 0) *sorted_flag = 1;
   __syncthreads();
   for (int j = threadIdx.x; j < T; j += kThreads) {
@@ -191,7 +192,7 @@ __device__ void check_ring_sorted(const float4* __restrict__ tgt, int T, int* so
 
 // A3/A4 exact brute-force 1-NN: every (32-query group, kNNChunk-target chunk) pair is one warp work item; all
 // lanes of a warp read the same target (broadcast 16-B load), each lane keeps its own query's best.
-__device__ void nn_brute(const float4* sel, unsigned long long* key, int nq, const float4* __restrict__ tgt, int T) {
+__device__ inline void nn_brute(const float4* sel, unsigned long long* key, int nq, const float4* __restrict__ tgt, int T) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nqg = (nq + 31) >> 5, nch = (T + kNNChunk - 1) / kNNChunk;
   for (int item = warp; item < nqg * nch; item += kWarps) {
@@ -363,7 +364,7 @@ __device__ __forceinline__ int col6(int a) { return a < 3 ? a : a + 3; }  // {0,
 // structural columns c = {0,1,2,6,7,8} are non-zero) and R = sig2 I:
 //   K = P H^T (H P H^T + R)^-1 = P[:,c] (A6 P[c,c] + sig2 I6)^-1 H6^T,   A6 = H6^T H6
 // so  K (r + H d) = P[:,c] M^-1 (b6 + A6 d_c)  and nothing larger than 6x6 is ever factorised.
-__device__ void form_M6(Smem& sm, double sig2, int idx, int stride) {
+__device__ inline void form_M6(Smem& sm, double sig2, int idx, int stride) {
   for (int t = idx; t < 36; t += stride) {
     const int a = t / 6, c = t % 6;
     double s = 0;
@@ -374,7 +375,7 @@ __device__ void form_M6(Smem& sm, double sig2, int idx, int stride) {
 }
 
 // linState (+) updateVec (KalmanFilter.hpp:71-81), thread 0
-__device__ void box_plus(Smem& sm) {
+__device__ inline void box_plus(Smem& sm) {
   double* l = sm.lin; const double* u = sm.upd;
   for (int i = 0; i < 3; ++i) {
     l[0 + i] += u[0 + i]; l[3 + i] += u[3 + i]; l[10 + i] += u[9 + i]; l[13 + i] += u[12 + i]; l[16 + i] += u[15 + i];

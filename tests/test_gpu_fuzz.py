@@ -219,3 +219,30 @@ def test_associate_reuses_indices_across_calls_icp_freq2(gpu, ob, golden_batch):
         tg, qg, itg, cvg = gpu.estimate_transform(u["surf_flat"], u["corner_sharp"], t0, q0)
         assert (itg, cvg) == (ito, cvo)
         assert np.abs(tg - to).max() <= 1e-4 and 2 * np.arccos(min(1.0, abs(float(np.dot(qg, qo))))) <= 1e-4
+
+
+def test_update_map_stays_on_device(gpu, ob, synth):
+    """Row F1 without the round trip: lins_gpu_update_map_ex with lin_state = NULL (the posterior lins_gpu_ieskf left on
+    the device) and no read-back must install exactly the map the host-visible call installs — checked through the next
+    scan's association against the oracle's updatePointCloud (StateEstimator.hpp:1116-1161)."""
+    prm = ob.LinsParams.shipped()
+    gpu.set_params(prm)
+    for seed in (9, 10):
+        b = synth.generate("config3", n=1, seed0=seed)
+        u = b.unit(0)
+        ns, nc = b.extra["new_surf_less_flat"], b.extra["new_corner_less_sharp"]
+        o = ob.Oracle(prm, use_kdtree=False)
+        for o_ in (o, gpu):
+            o_.set_map(u["surf_less_flat"], u["corner_less_sharp"])
+        sg, cg, rg = gpu.ieskf(u["surf_flat"], u["corner_sharp"], u["state"], u["cov"])
+        assert not rg.diverged
+        s1, c1, rep1 = o.update_map(ns, nc, sg)
+        assert gpu.update_map_device(ns, nc) == rep1 is True      # device posterior, nothing copied back
+        go, oo = gpu.associate(u["surf_flat"], u["corner_sharp"], u["state"], 0), o.associate(u["surf_flat"], u["corner_sharp"], u["state"], 0)
+        assert np.array_equal(go["surf_ind"], oo["surf_ind"]) and np.array_equal(go["corner_ind"], oo["corner_ind"])
+        assert np.array_equal(go["surf_mask"], oo["surf_mask"]) and np.array_equal(go["corner_mask"], oo["corner_mask"])
+        # explicit state + guard failure (map advances, index does not), still without read-back
+        s1, c1, rep1 = o.update_map(ns[:60], nc[:4], sg)
+        assert gpu.update_map_device(ns[:60], nc[:4], sg) == rep1 is False
+        go, oo = gpu.associate(u["surf_flat"], u["corner_sharp"], u["state"], 0), o.associate(u["surf_flat"], u["corner_sharp"], u["state"], 0)
+        assert np.array_equal(go["surf_ind"], oo["surf_ind"]) and np.array_equal(go["corner_ind"], oo["corner_ind"])

@@ -4,5 +4,4 @@ set -e
 cd "$(dirname "$0")/.."
 name=$1; shift
 mkdir -p variants
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 -shared -Xcompiler -fPIC "$@" \
-  -o variants/liblins_gpu_$name.so "lins---lidar-inertial-slam_b200/csrc/cuda/lins_gpu.cu"
+python tools/build_variant.py "$name" "$@"

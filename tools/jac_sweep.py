@@ -24,6 +24,24 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     ns = int(b.offsets["surf_flat"][-1]); nc = int(b.offsets["corner_sharp"][-1])
     byts = 76 * ns + 56 * nc + 384 * b.n
     print("variant %s: %.1f us  %.0f GB/s algorithmic" % (os.environ.get("LINS_JAC_VARIANT", "0"), ms * 1e3, byts / ms / 1e6))
+    if os.environ.get("LINS_GATHER_CAL"):
+        # calibration: what a pure random 16-B gather (one 32-B DRAM sector per access) over a working set of the same size
+        # reaches on this GPU — the access pattern that bounds the Jacobian kernel's target gathers
+        n = 408 * 1000 * 1000 // 16
+        table = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+        m = 8 * 1000 * 1000
+        idx = torch.randint(0, n, (m,), device="cuda")
+        out = torch.empty((m, 4), dtype=torch.float32, device="cuda")
+        for _ in range(3):
+            torch.index_select(table, 0, idx, out=out)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(10):
+            torch.index_select(table, 0, idx, out=out)
+        e.record(); torch.cuda.synchronize()
+        gms = a.elapsed_time(e) / 10
+        print("random 16-B gather calibration: %.1f us for %d accesses -> %.0f GB/s of 32-B sectors (+ %.0f GB/s of index reads and output writes)" % (
+            gms * 1e3, m, 32 * m / gms / 1e6, (8 + 16) * m / gms / 1e6))
 else:
     for v in sys.argv[1:] or ["0", "1", "2", "3", "4"]:
         env = dict(os.environ, LINS_JAC_VARIANT=v)
