@@ -449,7 +449,7 @@ def main():
     mapping_ms = (time.perf_counter() - t0) * 1e3 / mreps
     nq_map = len(mu.corner_last) + len(mu.surf_last)
     dist_evals = (len(mu.corner_last) * len(mu.corner_map) + len(mu.surf_last) * len(mu.surf_map)) * mrep.iters
-    mapping = {"what": "lins_gpu_scan2map (lidar_mapping_node.cpp:1635-1652): exact brute-force 5-NN + line / plane fits + LM, host buffers in / out",
+    mapping = {"what": "lins_gpu_scan2map (lidar_mapping_node.cpp:1635-1652): exact hashed-grid 5-NN + line / plane fits + the LM loop on the device (one D2H + one sync per call), host buffers in / out",
                "map_points": int(len(mu.corner_map) + len(mu.surf_map)), "feature_points": int(nq_map), "lm_iterations": int(mrep.iters),
                "converged": int(mrep.converged), "ms_per_call": mapping_ms, "distance_evaluations_per_s": dist_evals / (mapping_ms * 1e-3),
                "translation_error_m": {"before": float(np.abs(mu.guess[3:] - mu.truth[3:]).max()), "after": float(np.abs(mT[3:] - mu.truth[3:]).max())}}

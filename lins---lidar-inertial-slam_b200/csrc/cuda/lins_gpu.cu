@@ -12,6 +12,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -586,6 +587,16 @@ struct lins_ctx {
   struct MapState {
     DevBuf<float4> map_c, map_s, q_c, q_s;
     int n_map_c = -1, n_map_s = -1;
+    struct Grid {  // hashed uniform grid of one map cloud (lins_map.cuh)
+      DevBuf<float4> sorted;
+      DevBuf<int> start, count, cursor;
+      lins_map::GridIndex index;
+      int n = 0;
+      void release() { sorted.release(); start.release(); count.release(); cursor.release(); }
+    } grid_c, grid_s;
+    DevBuf<lins_map::MapLoopState> loop;   // device-resident state of one scan2map call
+    PinBuf<lins_map::MapLoopState> h_loop;
+    DevBuf<lins_map::PassConsts> consts;   // sin / cos + translation of the pass being run
     DevBuf<float> part_d;
     DevBuf<int> part_i;
     DevBuf<double> partial;
@@ -594,6 +605,7 @@ struct lins_ctx {
     DevBuf<float> coeff_c, coeff_s;
     DevBuf<uint8_t> mask_c, mask_s;
     void release() {
+      grid_c.release(); grid_s.release(); loop.release(); h_loop.release(); consts.release();
       map_c.release(); map_s.release(); q_c.release(); q_s.release(); part_d.release(); part_i.release(); partial.release();
       h_partial.release(); knn_c.release(); knn_s.release(); coeff_c.release(); coeff_s.release(); mask_c.release(); mask_s.release();
     }
@@ -1129,38 +1141,80 @@ int lins_gpu_debug_phase_cycles(lins_ctx* ctx, int enable, long long* out) {
 // ---- row F2: the mapping node's scan-to-map refinement (lidar_mapping_node.cpp:1635-1652) --------------------------------
 namespace {
 
-int map_upload(lins_ctx* ctx, DevBuf<float4>& dst, const lins_point* src, int n) {
-  CK(dst.reserve((size_t)n + 1));
-  if (n > 0) {
-    CK(ctx->h_tmp.reserve((size_t)n + 1));
-    CK(cudaStreamSynchronize(ctx->stream));  // the staging buffer may still feed an earlier copy
-    pack_into(ctx->h_tmp.p, src, n);
-    CK(cudaMemcpyAsync(dst.p, ctx->h_tmp.p, sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-  }
+// pack + queue the H2D of two clouds through the pinned staging (no stream synchronisation: see tmp_staging_wait)
+int map_upload2(lins_ctx* ctx, DevBuf<float4>& dst_a, const lins_point* a, int na, DevBuf<float4>& dst_b, const lins_point* b, int nb) {
+  CK(dst_a.reserve((size_t)na + 1)); CK(dst_b.reserve((size_t)nb + 1));
+  if (na + nb == 0) return LINS_OK;
+  CK(tmp_staging_wait(ctx));
+  CK(ctx->h_tmp.reserve((size_t)na + nb + 1));
+  pack_into(ctx->h_tmp.p, a, na);
+  pack_into(ctx->h_tmp.p + na, b, nb);
+  if (na) CK(cudaMemcpyAsync(dst_a.p, ctx->h_tmp.p, sizeof(float4) * (size_t)na, cudaMemcpyHostToDevice, ctx->stream));
+  if (nb) CK(cudaMemcpyAsync(dst_b.p, ctx->h_tmp.p + na, sizeof(float4) * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+  CK(tmp_staging_mark(ctx));
   return LINS_OK;
 }
 
-// one cornerOptimization + surfOptimization pass at T; AtA (6x6) / AtB (6) in f32 and the number of selected points
-int map_pass(lins_ctx* ctx, int nc, int ns, const float* T, bool dense, float* AtA, float* AtB, int* n_sel) {
-  using namespace lins_map;
-  lins_ctx::MapState& m = ctx->mp;
-  PassConsts pc;
+lins_map::PassConsts host_pass_consts(const float* T) {  // libm sin / cos in f32, like the reference (:579-592, :1527-1532)
+  lins_map::PassConsts pc;
   pc.cRoll = std::cos(T[0]); pc.sRoll = std::sin(T[0]); pc.cPitch = std::cos(T[1]); pc.sPitch = std::sin(T[1]);
   pc.cYaw = std::cos(T[2]); pc.sYaw = std::sin(T[2]); pc.tX = T[3]; pc.tY = T[4]; pc.tZ = T[5];
   pc.srx = std::sin(T[0]); pc.crx = std::cos(T[0]); pc.sry = std::sin(T[1]); pc.cry = std::cos(T[1]);
   pc.srz = std::sin(T[2]); pc.crz = std::cos(T[2]);
+  return pc;
+}
+
+// which 5-NN search a pass uses: the hashed grid (exact for every point that can be accepted) or the brute-force slices
+// (exact for every point).  LINS_MAP_KNN=grid|brute overrides the caller's default.
+bool map_use_grid(bool dflt) {
+  const char* e = std::getenv("LINS_MAP_KNN");  // (read per call: tests flip it between calls)
+  return !e || !*e ? dflt : std::strcmp(e, "grid") == 0;
+}
+
+// bucket-sort one map cloud into its grid (≙ kdtree*FromMap->setInputCloud, :1637-1638)
+int map_build_grid(lins_ctx* ctx, lins_ctx::MapState::Grid& g, const float4* map, int n, const lins_point* host_pts) {
+  using namespace lins_map;
+  g.n = n;
+  if (n <= 0) return LINS_OK;
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f};
+  for (int i = 0; i < n; ++i) {  // origin = the finite minimum (cells are addressed by hash: the extent does not matter)
+    const float v[3] = {host_pts[i].x, host_pts[i].y, host_pts[i].z};
+    for (int k = 0; k < 3; ++k) if (v[k] == v[k] && std::fabs(v[k]) < 1.0e30f && v[k] < mn[k]) mn[k] = v[k];
+  }
+  for (int k = 0; k < 3; ++k) if (!(mn[k] < 3.0e38f)) mn[k] = 0.f;
+  unsigned nb = 4096;
+  while (nb < 2u * (unsigned)n && nb < (1u << 24)) nb <<= 1;
+  CK(g.start.reserve((size_t)nb + 2)); CK(g.count.reserve((size_t)nb + 2)); CK(g.cursor.reserve((size_t)nb + 2)); CK(g.sorted.reserve((size_t)n + 1));
+  GridIndex gi;
+  gi.pts = g.sorted.p; gi.start = g.start.p; gi.mask = nb - 1; gi.ox = mn[0]; gi.oy = mn[1]; gi.oz = mn[2];
+  g.index = gi;
+  CK(cudaMemsetAsync(g.count.p, 0, sizeof(int) * nb, ctx->stream));
+  lins_grid_count_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(map, n, gi, g.count.p);
+  lins_grid_scan_kernel<<<1, 1024, 0, ctx->stream>>>(g.count.p, g.start.p, g.cursor.p, (int)nb);
+  lins_grid_scatter_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(map, n, gi, g.cursor.p, g.sorted.p);
+  CK(cudaGetLastError());
+  ctx->launches += 3;
+  return LINS_OK;
+}
+
+// queue one cornerOptimization + surfOptimization pass (5-NN, fits, block partials) that reads its constants from
+// m.consts (device); nothing is synchronised.  Returns the number of partial blocks.
+int map_queue_pass(lins_ctx* ctx, int nc, int ns, bool dense, bool grid, const int* done, int* nblocks_out) {
+  using namespace lins_map;
+  lins_ctx::MapState& m = ctx->mp;
   const int qb[2] = {(nc + kKnnThreads - 1) / kKnnThreads, (ns + kKnnThreads - 1) / kKnnThreads};
   const int nq[2] = {nc, ns}, nm[2] = {std::max(m.n_map_c, 0), std::max(m.n_map_s, 0)};
   const float4* q[2] = {m.q_c.p, m.q_s.p};
   const float4* mp[2] = {m.map_c.p, m.map_s.p};
+  const lins_ctx::MapState::Grid* gr[2] = {&m.grid_c, &m.grid_s};
   int slices[2], slice_len[2];
   size_t part = 0;
   for (int k = 0; k < 2; ++k) {
-    // enough (query block, map slice) pairs for ~8 CTAs per SM (the scan is latency bound: profiles/r01_map_*); a slice
-    // is at least 256 map points
+    // brute force: enough (query block, map slice) pairs for ~8 CTAs per SM (the scan is latency bound: profiles/r01_map_*);
+    // a slice is at least 256 map points.  grid: one list per query
     int S = qb[k] > 0 ? (8 * ctx->sm_count + qb[k] - 1) / qb[k] : 1;
     S = std::max(1, std::min(S, std::min(64, (nm[k] + 255) / 256)));
+    if (grid) S = 1;
     slices[k] = S;
     slice_len[k] = std::max(1, (nm[k] + S - 1) / S);
     part = std::max(part, (size_t)nq[k] * S * 5);
@@ -1174,38 +1228,28 @@ int map_pass(lins_ctx* ctx, int nc, int ns, const float* T, bool dense, float* A
   }
   for (int k = 0; k < 2; ++k) {
     if (nq[k] == 0) continue;
-    lins_map_knn_kernel<<<dim3(qb[k], slices[k]), kKnnThreads, 0, ctx->stream>>>(q[k], nq[k], mp[k], nm[k], slice_len[k], pc, m.part_d.p, m.part_i.p);
+    if (grid && nm[k] > 0)
+      lins_map_knn_grid_kernel<<<(nq[k] + kGridKnnWarps - 1) / kGridKnnWarps, kGridKnnWarps * 32, 0, ctx->stream>>>(q[k], nq[k], gr[k]->index, m.consts.p, done, m.part_d.p, m.part_i.p);
+    else
+      lins_map_knn_kernel<<<dim3(qb[k], slices[k]), kKnnThreads, 0, ctx->stream>>>(q[k], nq[k], mp[k], nm[k], slice_len[k], m.consts.p, done, m.part_d.p, m.part_i.p);
     double* partial = m.partial.p + (size_t)(k == 0 ? 0 : qb[0]) * (kRowAcc + 1);
     if (k == 0)
-      lins_map_fit_kernel<true><<<qb[k], kFitThreads, 0, ctx->stream>>>(q[k], nq[k], mp[k], slices[k], m.part_d.p, m.part_i.p, pc, dense ? m.knn_c.p : nullptr,
+      lins_map_fit_kernel<true><<<qb[k], kFitThreads, 0, ctx->stream>>>(q[k], nq[k], mp[k], slices[k], m.part_d.p, m.part_i.p, m.consts.p, done, dense ? m.knn_c.p : nullptr,
                                                                        dense ? m.coeff_c.p : nullptr, dense ? m.mask_c.p : nullptr, partial);
     else
-      lins_map_fit_kernel<false><<<qb[k], kFitThreads, 0, ctx->stream>>>(q[k], nq[k], mp[k], slices[k], m.part_d.p, m.part_i.p, pc, dense ? m.knn_s.p : nullptr,
+      lins_map_fit_kernel<false><<<qb[k], kFitThreads, 0, ctx->stream>>>(q[k], nq[k], mp[k], slices[k], m.part_d.p, m.part_i.p, m.consts.p, done, dense ? m.knn_s.p : nullptr,
                                                                         dense ? m.coeff_s.p : nullptr, dense ? m.mask_s.p : nullptr, partial);
     CK(cudaGetLastError());
     ctx->launches += 2;
   }
-  double acc[kRowAcc + 1] = {0};
-  if (nblocks > 0) {
-    CK(cudaMemcpyAsync(m.h_partial.p, m.partial.p, sizeof(double) * (size_t)nblocks * (kRowAcc + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (int b = 0; b < nblocks; ++b)  // fixed order: corner blocks, then surf blocks (laserCloudOri's order)
-      for (int k = 0; k <= kRowAcc; ++k) acc[k] += m.h_partial.p[(size_t)b * (kRowAcc + 1) + k];
-  }
-  int k = 0;
-  for (int a = 0; a < 6; ++a)
-    for (int c = a; c < 6; ++c) { AtA[a * 6 + c] = (float)acc[k]; AtA[c * 6 + a] = (float)acc[k]; ++k; }
-  for (int a = 0; a < 6; ++a) AtB[a] = (float)acc[21 + a];
-  *n_sel = (int)acc[kRowAcc];
+  *nblocks_out = nblocks;
   return LINS_OK;
 }
 
 int map_stage_queries(lins_ctx* ctx, const lins_point* corner, int nc, const lins_point* surf, int ns) {
   if (nc < 0 || ns < 0 || (nc > 0 && !corner) || (ns > 0 && !surf)) return fail(ctx, LINS_E_INVALID, "bad feature clouds");
   if (ctx->mp.n_map_c < 0) return fail(ctx, LINS_E_NOMAP, "lins_gpu_map_set has not been called");
-  int rc = map_upload(ctx, ctx->mp.q_c, corner, nc);
-  if (rc != LINS_OK) return rc;
-  return map_upload(ctx, ctx->mp.q_s, surf, ns);
+  return map_upload2(ctx, ctx->mp.q_c, corner, nc, ctx->mp.q_s, surf, ns);
 }
 
 }  // namespace
@@ -1214,43 +1258,57 @@ int lins_gpu_map_set(lins_ctx* ctx, const lins_point* corner, int nc, const lins
   if (!ctx) return LINS_E_INVALID;
   if (nc < 0 || ns < 0 || (nc > 0 && !corner) || (ns > 0 && !surf)) return fail(ctx, LINS_E_INVALID, "bad map clouds");
   CK(cudaSetDevice(ctx->device));
-  int rc = map_upload(ctx, ctx->mp.map_c, corner, nc);
-  if (rc != LINS_OK) return rc;
-  rc = map_upload(ctx, ctx->mp.map_s, surf, ns);
+  int rc = map_upload2(ctx, ctx->mp.map_c, corner, nc, ctx->mp.map_s, surf, ns);
   if (rc != LINS_OK) return rc;
   ctx->mp.n_map_c = nc; ctx->mp.n_map_s = ns;
-  return LINS_OK;
+  rc = map_build_grid(ctx, ctx->mp.grid_c, ctx->mp.map_c.p, nc, corner);
+  if (rc != LINS_OK) return rc;
+  return map_build_grid(ctx, ctx->mp.grid_s, ctx->mp.map_s.p, ns, surf);
 }
 
 int lins_gpu_scan2map(lins_ctx* ctx, const lins_point* corner, int nc, const lins_point* surf, int ns, float* T, lins_map_report* rep) {
   if (!ctx) return LINS_E_INVALID;
   if (!T) return fail(ctx, LINS_E_INVALID, "null transform");
   CK(cudaSetDevice(ctx->device));
+  using namespace lins_map;
   lins_map_report r;
   std::memset(&r, 0, sizeof(r));
-  if (ctx->mp.n_map_c < 0) return fail(ctx, LINS_E_NOMAP, "lins_gpu_map_set has not been called");
-  if (!(ctx->mp.n_map_c > 10 && ctx->mp.n_map_s > 100)) {  // :1636
+  lins_ctx::MapState& m = ctx->mp;
+  if (m.n_map_c < 0) return fail(ctx, LINS_E_NOMAP, "lins_gpu_map_set has not been called");
+  if (!(m.n_map_c > 10 && m.n_map_s > 100)) {  // :1636
     r.skipped = 1;
     if (rep) *rep = r;
     return LINS_OK;
   }
   int rc = map_stage_queries(ctx, corner, nc, surf, ns);
   if (rc != LINS_OK) return rc;
-  lins::mapping::LmState st;
-  for (int iter = 0; iter < LINS_MAP_MAX_ITER; ++iter) {
-    float AtA[36], AtB[6];
-    int n_sel = 0;
-    rc = map_pass(ctx, nc, ns, T, false, AtA, AtB, &n_sel);
-    if (rc != LINS_OK) return rc;
-    r.iters = iter + 1;
-    r.n_sel[iter] = n_sel;
-    if (n_sel < 50) continue;  // LMOptimization returns false before touching the transform (:1535-1537)
-    float dR = 0, dT = 0;
-    const bool conv = lins::mapping::lm_step(AtA, AtB, iter, T, st, dR, dT);
-    r.delta_r[iter] = dR; r.delta_t[iter] = dT;
-    r.degenerate = st.isDegenerate ? 1 : 0;
-    if (conv) { r.converged = 1; break; }
+  // The whole iteration loop (:1640-1648) is queued up front: transformTobeMapped, matP / isDegenerate and the report live
+  // on the device (MapLoopState); the first pass uses libm sin / cos of the caller's transform (bit-identical to the
+  // reference's first pass), later ones the constants the LM kernel derived on the device.
+  if (!m.loop.p) {  // isDegenerate / matP are members of the reference's mapping node (:226-227, :395-396): they survive the
+    CK(m.loop.reserve(1));  // calls — a call whose first pass selects < 50 points keeps using the previous scan's values
+    CK(cudaMemsetAsync(m.loop.p, 0, sizeof(MapLoopState), ctx->stream));
   }
+  CK(m.h_loop.reserve(1)); CK(m.consts.reserve(1));
+  const PassConsts pc0 = host_pass_consts(T);
+  CK(cudaMemcpyAsync(m.loop.p, T, sizeof(float) * 6, cudaMemcpyHostToDevice, ctx->stream));  // (pageable sources: staged before the call returns)
+  CK(cudaMemsetAsync(reinterpret_cast<char*>(m.loop.p) + offsetof(MapLoopState, done), 0, sizeof(MapLoopState) - offsetof(MapLoopState, done), ctx->stream));
+  CK(cudaMemcpyAsync(m.consts.p, &pc0, sizeof(pc0), cudaMemcpyHostToDevice, ctx->stream));
+  const bool grid = map_use_grid(true);
+  for (int iter = 0; iter < LINS_MAP_MAX_ITER; ++iter) {
+    int nblocks = 0;
+    rc = map_queue_pass(ctx, nc, ns, false, grid, &m.loop.p->done, &nblocks);
+    if (rc != LINS_OK) return rc;
+    lins_map_lm_kernel<<<1, 32, 0, ctx->stream>>>(m.partial.p, nblocks, iter, m.loop.p, m.consts.p);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  CK(cudaMemcpyAsync(m.h_loop.p, m.loop.p, sizeof(MapLoopState), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const MapLoopState& st = *m.h_loop.p;
+  for (int i = 0; i < 6; ++i) T[i] = st.T[i];
+  r.iters = st.iters; r.converged = st.converged; r.degenerate = st.isDegenerate;
+  for (int i = 0; i < LINS_MAP_MAX_ITER; ++i) { r.n_sel[i] = st.n_sel[i]; r.delta_r[i] = st.delta_r[i]; r.delta_t[i] = st.delta_t[i]; }
   if (rep) *rep = r;
   return LINS_OK;
 }
@@ -1262,11 +1320,14 @@ int lins_gpu_map_associate(lins_ctx* ctx, const lins_point* corner, int nc, cons
   CK(cudaSetDevice(ctx->device));
   int rc = map_stage_queries(ctx, corner, nc, surf, ns);
   if (rc != LINS_OK) return rc;
-  float AtA[36], AtB[6];
-  int n_sel = 0;
-  rc = map_pass(ctx, nc, ns, T, true, AtA, AtB, &n_sel);
-  if (rc != LINS_OK) return rc;
   lins_ctx::MapState& m = ctx->mp;
+  CK(m.consts.reserve(1));
+  const lins_map::PassConsts pc = host_pass_consts(T);
+  CK(cudaMemcpyAsync(m.consts.p, &pc, sizeof(pc), cudaMemcpyHostToDevice, ctx->stream));
+  int nblocks = 0;
+  // the parity hook: brute force by default (exact neighbours for EVERY point, also those the 1 m gate rejects)
+  rc = map_queue_pass(ctx, nc, ns, true, map_use_grid(false), nullptr, &nblocks);
+  if (rc != LINS_OK) return rc;
   if (cknn && nc) CK(cudaMemcpyAsync(cknn, m.knn_c.p, sizeof(int32_t) * 5 * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));
   if (sknn && ns) CK(cudaMemcpyAsync(sknn, m.knn_s.p, sizeof(int32_t) * 5 * (size_t)ns, cudaMemcpyDeviceToHost, ctx->stream));
   if (ccoeff && nc) CK(cudaMemcpyAsync(ccoeff, m.coeff_c.p, sizeof(float) * 4 * (size_t)nc, cudaMemcpyDeviceToHost, ctx->stream));

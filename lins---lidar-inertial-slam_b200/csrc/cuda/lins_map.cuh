@@ -63,8 +63,10 @@ struct Top5 {
 
 // grid (query blocks, slices).  part_d / part_i: [n_q][n_slices][5]
 __global__ void __launch_bounds__(kKnnThreads) lins_map_knn_kernel(const float4* __restrict__ q, int n_q, const float4* __restrict__ map, int n_map,
-                                                                   int slice_len, PassConsts pc, float* __restrict__ part_d,
-                                                                   int* __restrict__ part_i) {
+                                                                   int slice_len, const PassConsts* __restrict__ pcp, const int* __restrict__ done,
+                                                                   float* __restrict__ part_d, int* __restrict__ part_i) {
+  if (done && *done) return;  // (the queued tail of a converged scan2map loop)
+  const PassConsts pc = *pcp;
   __shared__ float4 tile[kTile];
   const int qi = blockIdx.x * kKnnThreads + threadIdx.x;
   const int slice = blockIdx.y, n_slices = gridDim.y;
@@ -181,9 +183,12 @@ __device__ __forceinline__ void lm_row(const float4 po, const float* c, const Pa
 template <bool CORNER>
 __global__ void __launch_bounds__(kFitThreads) lins_map_fit_kernel(const float4* __restrict__ q, int n_q, const float4* __restrict__ map,
                                                                    int n_slices, const float* __restrict__ part_d,
-                                                                   const int* __restrict__ part_i, PassConsts pc, int32_t* __restrict__ knn_out,
+                                                                   const int* __restrict__ part_i, const PassConsts* __restrict__ pcp,
+                                                                   const int* __restrict__ done, int32_t* __restrict__ knn_out,
                                                                    float* __restrict__ coeff_out, uint8_t* __restrict__ mask_out,
                                                                    double* __restrict__ partial) {
+  if (done && *done) return;
+  const PassConsts pc = *pcp;
   const int qi = blockIdx.x * kFitThreads + threadIdx.x;
   double acc[kRowAcc];
 #pragma unroll
@@ -254,6 +259,204 @@ __global__ void __launch_bounds__(kFitThreads) lins_map_fit_kernel(const float4*
     for (int w = 0; w < kFitThreads / 32; ++w) c += wcnt[w];
     partial[(size_t)blockIdx.x * (kRowAcc + 1) + kRowAcc] = (double)c;
   }
+}
+
+
+// =====================================================================================================================
+// Reference-scale path: exact 5-NN through a hashed uniform grid + the LM step on the device.
+//
+// Grid.  The reference accepts a feature point only if its FIFTH neighbour lies within 1 m (pointSearchSqDis[4] < 1.0,
+// lidar_mapping_node.cpp:1374, :1481), so the only neighbours that matter are those within 1 m, and every map point
+// within 1 m of a query lies in the 3 x 3 x 3 block of 1 m cells around the query's cell.  lins_gpu_map_set bucket-sorts
+// the map by hash(cell) (the role of kdtree*FromMap->setInputCloud, :1637-1638); a query warp gives one cell of the
+// block to each of 27 lanes (cells that hash to the same bucket are visited once), every lane keeps the five smallest
+// (distance, index) keys of its bucket — points of other cells that share the bucket are just extra candidates — and a
+// five-round warp minimum merges the lanes.  If the merged fifth distance is < 1, all five are exact (any closer point
+// would have been in the block); otherwise the true fifth distance is >= 1 as well and the point is rejected either
+// way.  Keys are (f32 distance bits, index), so ties resolve to the lower index exactly like the brute-force scan.
+//
+// LM loop.  scan2map keeps transformTobeMapped, matP / isDegenerate and the report on the device (MapLoopState): per
+// iteration the 5-NN kernel, the fit / reduction kernel and a one-warp kernel that sums the block partials in a fixed
+// order, takes the 6 x 6 step (LMOptimization :1598-1632, lins_cv_small.hpp) and prepares the next iteration's sin / cos;
+// once it sets `done`, the launches still queued return at once.  One D2H and one synchronisation per call.
+constexpr float kGridCell = 1.0f;  // >= the 1 m acceptance radius
+constexpr int kGridKnnWarps = 4;   // query warps per CTA
+
+struct GridIndex {
+  const float4* pts;      // map points bucket-sorted: (x, y, z, original index as int bits)
+  const int* start;       // [n_buckets + 1]
+  unsigned mask;          // n_buckets - 1 (power of two)
+  float ox, oy, oz;       // grid origin
+};
+__device__ __forceinline__ unsigned grid_hash(int ix, int iy, int iz) {
+  return ((unsigned)ix * 73856093u) ^ ((unsigned)iy * 19349663u) ^ ((unsigned)iz * 83492791u);
+}
+__device__ __forceinline__ void grid_cell(const GridIndex& g, float x, float y, float z, int& ix, int& iy, int& iz) {
+  ix = (int)floorf((x - g.ox) * (1.0f / kGridCell)); iy = (int)floorf((y - g.oy) * (1.0f / kGridCell)); iz = (int)floorf((z - g.oz) * (1.0f / kGridCell));
+}
+// counting sort of the map by bucket: count, (host-launched) scan, scatter
+__global__ void lins_grid_count_kernel(const float4* __restrict__ map, int n, GridIndex g, int* __restrict__ count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(&map[i]);
+  int ix, iy, iz;
+  grid_cell(g, p.x, p.y, p.z, ix, iy, iz);
+  atomicAdd(&count[grid_hash(ix, iy, iz) & g.mask], 1);
+}
+// exclusive scan of count[0..n) -> start[0..n], one CTA (runs once per lins_gpu_map_set)
+__global__ void __launch_bounds__(1024) lins_grid_scan_kernel(const int* __restrict__ count, int* __restrict__ start, int* __restrict__ cursor, int n) {
+  __shared__ int part[1024];
+  const int per = (n + 1023) / 1024, lo = threadIdx.x * per, hi = min(n, lo + per);
+  int s = 0;
+  for (int i = lo; i < hi; ++i) s += count[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { int run = 0; for (int i = 0; i < 1024; ++i) { const int v = part[i]; part[i] = run; run += v; } start[n] = run; }
+  __syncthreads();
+  int run = part[threadIdx.x];
+  for (int i = lo; i < hi; ++i) { start[i] = run; cursor[i] = run; run += count[i]; }
+}
+__global__ void lins_grid_scatter_kernel(const float4* __restrict__ map, int n, GridIndex g, int* __restrict__ cursor, float4* __restrict__ sorted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(&map[i]);
+  int ix, iy, iz;
+  grid_cell(g, p.x, p.y, p.z, ix, iy, iz);
+  const int pos = atomicAdd(&cursor[grid_hash(ix, iy, iz) & g.mask], 1);
+  sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+}
+
+struct Top5K {  // five smallest (distance bits, index) keys, ascending
+  unsigned long long k[5];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) k[j] = 0xFFFFFFFFFFFFFFFFull;
+  }
+  __device__ __forceinline__ void insert(unsigned long long key) {
+    if (!(key < k[4])) return;
+    k[4] = key;
+#pragma unroll
+    for (int j = 4; j > 0; --j)
+      if (k[j] < k[j - 1]) { const unsigned long long t = k[j]; k[j] = k[j - 1]; k[j - 1] = t; }
+  }
+};
+
+// one warp per query; part_d / part_i: [n_q][1][5] (a single "slice" for lins_map_fit_kernel)
+__global__ void __launch_bounds__(kGridKnnWarps * 32) lins_map_knn_grid_kernel(const float4* __restrict__ q, int n_q, GridIndex g,
+                                                                               const PassConsts* __restrict__ pcp, const int* __restrict__ done,
+                                                                               float* __restrict__ part_d, int* __restrict__ part_i) {
+  if (done && *done) return;
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * kGridKnnWarps + (threadIdx.x >> 5);
+  if (qi >= n_q) return;
+  const PassConsts pc = *pcp;
+  const float3 s = associate_to_map(__ldg(&q[qi]), pc);
+  int cx, cy, cz;
+  grid_cell(g, s.x, s.y, s.z, cx, cy, cz);
+  unsigned b = 0xFFFFFF00u + (unsigned)lane;  // lanes 27..31: a bucket id nobody shares, never scanned
+  if (lane < 27) b = grid_hash(cx + lane % 3 - 1, cy + (lane / 3) % 3 - 1, cz + lane / 9 - 1) & g.mask;
+  const unsigned same = __match_any_sync(0xffffffffu, b);
+  const bool mine = lane < 27 && (__ffs(same) - 1) == lane;  // cells of the block that share a bucket are visited once
+  Top5K t;
+  t.init();
+  if (mine && s.x == s.x) {
+    const int p0 = g.start[b], p1 = g.start[b + 1];
+    for (int p = p0; p < p1; ++p) {
+      const float4 m = __ldg(&g.pts[p]);
+      const float dx = __fsub_rn(s.x, m.x), dy = __fsub_rn(s.y, m.y), dz = __fsub_rn(s.z, m.z);
+      const float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (dist == dist) t.insert(((unsigned long long)__float_as_uint(dist) << 32) | (unsigned)__float_as_int(m.w));
+    }
+  }
+  // five rounds: the smallest head among the lanes' ascending lists
+  int head = 0;
+  const size_t o = (size_t)qi * 5;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    const unsigned long long mykey = head < 5 ? t.k[0] : 0xFFFFFFFFFFFFFFFFull;
+    const unsigned hi = (unsigned)(mykey >> 32), lo = (unsigned)mykey;
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    if (hi == mhi && lo == mlo && mykey != 0xFFFFFFFFFFFFFFFFull) {  // unique keys: exactly one lane
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t.k[j] = t.k[j + 1];
+      t.k[4] = 0xFFFFFFFFFFFFFFFFull;
+      ++head;
+    }
+    if (lane == 0) {
+      const bool none = mhi == 0xffffffffu && mlo == 0xffffffffu;
+      part_d[o + r] = none ? __int_as_float(0x7f800000) : __uint_as_float(mhi);
+      part_i[o + r] = none ? -1 : (int)mlo;
+    }
+  }
+}
+
+// state of one scan2MapOptimization call on the device
+struct MapLoopState {
+  float T[6];            // transformTobeMapped
+  float matP[36];
+  int isDegenerate, done, iters, converged;
+  int n_sel[10];
+  float delta_r[10], delta_t[10];
+};
+
+__device__ __forceinline__ void pass_consts_from(const float* T, PassConsts& pc) {  // :579-592, :1527-1532 (f32 like the reference)
+  pc.cRoll = (float)cos((double)T[0]); pc.sRoll = (float)sin((double)T[0]);
+  pc.cPitch = (float)cos((double)T[1]); pc.sPitch = (float)sin((double)T[1]);
+  pc.cYaw = (float)cos((double)T[2]); pc.sYaw = (float)sin((double)T[2]);
+  pc.tX = T[3]; pc.tY = T[4]; pc.tZ = T[5];
+  pc.srx = pc.sRoll; pc.crx = pc.cRoll; pc.sry = pc.sPitch; pc.cry = pc.cPitch; pc.srz = pc.sYaw; pc.crz = pc.cYaw;
+}
+
+// one warp (the 6 x 6 step itself is one thread): block partials -> matAtA / matAtB (f32), the LM step, the next iteration's constants.  Every matrix lives
+// in shared memory (plain dynamically indexed loads / stores).
+__global__ void lins_map_lm_kernel(const double* __restrict__ partial, int nblocks, int iter, MapLoopState* __restrict__ st,
+                                   PassConsts* __restrict__ pc_next) {
+  if (blockIdx.x != 0 || st->done) return;
+  __shared__ double acc[kRowAcc + 1];
+  __shared__ float AtA[36], AtB[6], Aw[36], X[6], Ae[36], E[6], V[36], V2[36], Vc[36], Vinv[36], X2[6];
+  if (threadIdx.x <= kRowAcc) {  // lane k sums column k of the block partials, in a fixed order: corner blocks, then surf
+    double v = 0.0;               // blocks (laserCloudOri's order)
+    for (int b = 0; b < nblocks; ++b) v += partial[(size_t)b * (kRowAcc + 1) + threadIdx.x];
+    acc[threadIdx.x] = v;
+  }
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  int k = 0;
+  for (int a = 0; a < 6; ++a)
+    for (int c = a; c < 6; ++c) { AtA[a * 6 + c] = (float)acc[k]; AtA[c * 6 + a] = (float)acc[k]; ++k; }
+  for (int a = 0; a < 6; ++a) AtB[a] = (float)acc[21 + a];
+  const int n_sel = (int)acc[kRowAcc];
+  st->iters = iter + 1;
+  st->n_sel[iter] = n_sel;
+  if (n_sel < 50) return;  // LMOptimization returns false before touching the transform (:1535-1537)
+  for (int i = 0; i < 36; ++i) Aw[i] = AtA[i];
+  for (int i = 0; i < 6; ++i) X[i] = AtB[i];
+  if (!lins_cv::qr_solve<6, 6>(Aw, X)) for (int i = 0; i < 6; ++i) X[i] = 0.f;  // a failed cv::solve zeroes matX
+  if (iter == 0) {
+    for (int i = 0; i < 36; ++i) Ae[i] = AtA[i];
+    lins_cv::jacobi_eigen<6>(Ae, E, V);
+    for (int i = 0; i < 36; ++i) { V2[i] = V[i]; Vc[i] = V[i]; }
+    st->isDegenerate = 0;
+    for (int i = 5; i >= 0; --i) {
+      if (E[i] < 100.f) { for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0; st->isDegenerate = 1; }
+      else break;
+    }
+    if (!lins_cv::lu_invert<6>(Vc, Vinv)) for (int i = 0; i < 36; ++i) Vinv[i] = 0.f;
+    lins_cv::gemm<6, 6, 6>(Vinv, V2, st->matP);
+  }
+  if (st->isDegenerate) {
+    for (int i = 0; i < 6; ++i) X2[i] = X[i];
+    lins_cv::gemm<6, 6, 1>(st->matP, X2, X);
+  }
+  for (int i = 0; i < 6; ++i) st->T[i] += X[i];
+  const float r0 = X[0] * 57.29578f, r1 = X[1] * 57.29578f, r2 = X[2] * 57.29578f;  // pcl::rad2deg(float)
+  const float dR = (float)sqrt((double)r0 * (double)r0 + (double)r1 * (double)r1 + (double)r2 * (double)r2);
+  const float t0 = X[3] * 100, t1 = X[4] * 100, t2 = X[5] * 100;
+  const float dT = (float)sqrt((double)t0 * (double)t0 + (double)t1 * (double)t1 + (double)t2 * (double)t2);
+  st->delta_r[iter] = dR; st->delta_t[iter] = dT;
+  if (dR < 0.05 && dT < 0.05) { st->converged = 1; st->done = 1; return; }
+  pass_consts_from(st->T, *pc_next);
 }
 
 }  // namespace lins_map

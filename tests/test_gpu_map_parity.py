@@ -83,3 +83,33 @@ def test_map_edge_cases(gpu, ob):
     a = gpu.map_associate(g["corner_last"][:5], far, g["guess"])
     _same_pass(a, m.associate(g["corner_last"][:5], far, g["guess"]), "far queries")
     assert a["surf_mask"].sum() == 0
+
+
+@pytest.mark.parametrize("seed,kf", [(5, 50), (11, 25)])
+def test_grid_knn_equals_brute_force(gpu, ob, synth, seed, kf):
+    """The hashed-grid 5-NN that lins_gpu_scan2map uses (LINS_MAP_KNN=grid forces it for the dense parity hook too) must
+    give, for every point the 1 m gate can accept, exactly the brute-force neighbours / coefficients / masks; the points
+    whose fifth neighbour is farther than 1 m are rejected by both (lidar_mapping_node.cpp:1374, :1481)."""
+    u = synth.generate_map_unit("config3", seed=seed, n_keyframes=kf, sigma_t=0.1, sigma_r=0.01)
+    gpu.map_set(u.corner_map, u.surf_map)
+    old = os.environ.get("LINS_MAP_KNN")
+    try:
+        os.environ["LINS_MAP_KNN"] = "brute"
+        b = gpu.map_associate(u.corner_last, u.surf_last, u.guess)
+        os.environ["LINS_MAP_KNN"] = "grid"
+        g = gpu.map_associate(u.corner_last, u.surf_last, u.guess)
+    finally:
+        if old is None:
+            os.environ.pop("LINS_MAP_KNN", None)
+        else:
+            os.environ["LINS_MAP_KNN"] = old
+    for name, cloud, mp in (("corner", u.corner_last, u.corner_map), ("surf", u.surf_last, u.surf_map)):
+        assert np.array_equal(b[name + "_mask"], g[name + "_mask"])
+        assert np.array_equal(b[name + "_coeff"].view(np.uint32), g[name + "_coeff"].view(np.uint32))
+        # where the brute-force fifth neighbour is within 1 m the five indices agree exactly
+        m = ob.MapOracle(); m.set_map(u.corner_map, u.surf_map)
+        sel = b[name + "_mask"].astype(bool)
+        assert sel.sum() > 20
+        assert np.array_equal(b[name + "_knn"][sel], g[name + "_knn"][sel])
+        # and every index the grid returns is a real neighbour index
+        assert (g[name + "_knn"] >= -1).all() and (g[name + "_knn"] < len(mp)).all()
