@@ -128,8 +128,52 @@ def seq_lib():
         L.lins_seq_array.argtypes = [C.c_void_p, C.c_int]
         L.lins_seq_ints.restype = C.POINTER(C.c_int32)
         L.lins_seq_ints.argtypes = [C.c_void_p, C.c_int]
+        L.lins_seq_write_bag.argtypes = [C.POINTER(SynthCfg), C.c_uint64, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p]
+        L.lins_seq_run_bag.restype = C.c_void_p
+        L.lins_seq_run_bag.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         _SEQ = L
     return _SEQ
+
+
+def _seq_record(L, h):
+    n, ns = L.lins_seq_num_units(h), L.lins_seq_num_scans(h)
+    d = LinsBatchDesc()
+    L.lins_seq_desc(h, C.byref(d))
+    clouds, offsets = {}, {}
+    for k in Batch.FIELDS:
+        off = _copy(getattr(d, k + "_off"), n + 1, np.int32)
+        offsets[k] = off
+        clouds[k] = _copy(getattr(d, k), int(off[-1]), POINT_DTYPE)
+    arr = lambda which, cnt: np.ctypeslib.as_array(L.lins_seq_array(h, which), shape=(cnt,)).copy() if cnt else np.zeros(0)  # noqa: E731
+    ints = lambda which, cnt: np.ctypeslib.as_array(L.lins_seq_ints(h, which), shape=(cnt,)).copy() if cnt else np.zeros(0, np.int32)  # noqa: E731
+    units = Batch(clouds, offsets, _copy(d.state_in, n * 19, np.float64), _copy(d.cov_in, n * 324, np.float64), arr(1, n * 7)) if n else None
+    return dict(units=units, state_out=arr(0, n * 19).reshape(-1, 19), iters=ints(0, n), flags=ints(1, n), scan_index=ints(2, n),
+                status=ints(3, ns), global_est=arr(2, ns * 7).reshape(-1, 7), global_true=arr(3, ns * 7).reshape(-1, 7))
+
+
+def write_sequence_bag(path, config="config3", seed=1, n_scans=12, lidar_topic="/velodyne_points", imu_topic="/imu/data", **overrides):
+    """The synthetic drive of run_sequence written as a ROS1 bag (raw sweeps + IMU): no GPU needed."""
+    L = seq_lib()
+    kw = dict(CONFIGS[config])
+    kw.update(overrides)
+    cfg = SynthCfg(**kw)
+    rc = L.lins_seq_write_bag(C.byref(cfg), seed, n_scans, path.encode(), lidar_topic.encode(), imu_topic.encode())
+    if rc != 0:
+        raise RuntimeError(f"lins_seq_write_bag failed with {rc}")
+
+
+def run_bag(path, lidar_topic="/velodyne_points", imu_topic="/imu/data", max_scans=0, lidar_model=0, device=0):
+    """BASELINE.json configs[1] runner: replay a ROS1 bag (sensor_msgs/PointCloud2 + sensor_msgs/Imu) through image
+    projection, feature extraction and the GPU IESKF update, the way LinsFusion does (Estimator.cpp:123-284)."""
+    L = seq_lib()
+    err = C.c_int(0)
+    h = L.lins_seq_run_bag(path.encode(), lidar_topic.encode(), imu_topic.encode(), max_scans, lidar_model, device, C.byref(err))
+    if not h:
+        raise RuntimeError(f"lins_seq_run_bag failed with {err.value}")
+    try:
+        return _seq_record(L, h)
+    finally:
+        L.lins_seq_destroy(h)
 
 
 def run_sequence(config="config3", seed=1, n_scans=12, device=0, **overrides):
@@ -141,19 +185,7 @@ def run_sequence(config="config3", seed=1, n_scans=12, device=0, **overrides):
     cfg = SynthCfg(**kw)
     h = L.lins_seq_run(C.byref(cfg), seed, n_scans, device)
     try:
-        n, ns = L.lins_seq_num_units(h), L.lins_seq_num_scans(h)
-        d = LinsBatchDesc()
-        L.lins_seq_desc(h, C.byref(d))
-        clouds, offsets = {}, {}
-        for k in Batch.FIELDS:
-            off = _copy(getattr(d, k + "_off"), n + 1, np.int32)
-            offsets[k] = off
-            clouds[k] = _copy(getattr(d, k), int(off[-1]), POINT_DTYPE)
-        arr = lambda which, cnt: np.ctypeslib.as_array(L.lins_seq_array(h, which), shape=(cnt,)).copy() if cnt else np.zeros(0)  # noqa: E731
-        ints = lambda which, cnt: np.ctypeslib.as_array(L.lins_seq_ints(h, which), shape=(cnt,)).copy() if cnt else np.zeros(0, np.int32)  # noqa: E731
-        units = Batch(clouds, offsets, _copy(d.state_in, n * 19, np.float64), _copy(d.cov_in, n * 324, np.float64), arr(1, n * 7)) if n else None
-        return dict(units=units, state_out=arr(0, n * 19).reshape(-1, 19), iters=ints(0, n), flags=ints(1, n), scan_index=ints(2, n),
-                    status=ints(3, ns), global_est=arr(2, ns * 7).reshape(-1, 7), global_true=arr(3, ns * 7).reshape(-1, 7))
+        return _seq_record(L, h)
     finally:
         L.lins_seq_destroy(h)
 

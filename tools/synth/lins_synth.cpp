@@ -444,4 +444,52 @@ void lins_synth_map_unit_transforms(void* h, float* truth, float* guess) {
   std::memcpy(guess, u->guess, sizeof(u->guess));
 }
 
+// The product's CPU front end alone (csrc/host/image_projection.hpp + feature_extraction.hpp) on one raw sweep, for the
+// tests that check these restatements against an independent Python one (tests/pyfront.py).  Every output array has room
+// for `cap` entries (>= line_num * scan_num); counts: n[0] segmented, n[1] outlier, n[2] sharp, n[3] less sharp, n[4] flat,
+// n[5] less flat.
+int lins_frontend_run(const lins_point* raw, int n_raw, int lidar_model, int cap, lins_point* seg, lins_point* outlier, int32_t* start_ring,
+                      int32_t* end_ring, float* ori3, uint8_t* ground, uint32_t* col, float* range, lins_point* undist, lins_point* sharp,
+                      lins_point* less_sharp, lins_point* flat, lins_point* less_flat, int32_t* n) {
+  const LidarModel lm = lidar_model == 1 ? LidarModel::dense64() : LidarModel::vlp16();
+  Cloud in;
+  in.points.assign(raw, raw + n_raw);
+  ImageProjection ip(lm);
+  ip.process(in);
+  FeatureExtractor fe(lm);
+  ScanFeatures f;
+  fe.run(ip.segmentedCloud, ip.segMsg, f);
+  auto put = [&](const Cloud& c, lins_point* dst, int32_t& cnt) {
+    cnt = (int32_t)c.size();
+    std::memcpy(dst, c.points.data(), sizeof(lins_point) * std::min<size_t>(c.size(), (size_t)cap));
+  };
+  put(ip.segmentedCloud, seg, n[0]); put(ip.outlierCloud, outlier, n[1]);
+  put(f.cornerPointsSharp, sharp, n[2]); put(f.cornerPointsLessSharp, less_sharp, n[3]);
+  put(f.surfPointsFlat, flat, n[4]); put(f.surfPointsLessFlat, less_flat, n[5]);
+  int32_t nu = 0;
+  put(f.undistPointCloud, undist, nu);
+  for (int i = 0; i < lm.line_num; ++i) { start_ring[i] = ip.segMsg.startRingIndex[i]; end_ring[i] = ip.segMsg.endRingIndex[i]; }
+  ori3[0] = ip.segMsg.startOrientation; ori3[1] = ip.segMsg.endOrientation; ori3[2] = ip.segMsg.orientationDiff;
+  for (int i = 0; i < std::min(n[0], cap); ++i) { ground[i] = ip.segMsg.segmentedCloudGroundFlag[i]; col[i] = ip.segMsg.segmentedCloudColInd[i]; range[i] = ip.segMsg.segmentedCloudRange[i]; }
+  return 0;
+}
+
+// one simulated raw sweep of the seeded world (an input for lins_frontend_run): returns the number of points written
+int lins_synth_raw_sweep(const lins_synth_cfg* cfg, uint64_t seed, lins_point* out, int cap) {
+  Rng rng(seed);
+  const LidarModel lm = cfg->lidar == 1 ? LidarModel::dense64() : LidarModel::vlp16();
+  World w = make_world(rng, cfg->world);
+  Pose T0;
+  T0.R = math_utils::rpy2Quat(V3D(rng.uni(-0.02, 0.02), rng.uni(-0.02, 0.02), rng.uni(-M_PI, M_PI))).toRotationMatrix();
+  T0.p = V3D(rng.uni(-8, 8), rng.uni(-8, 8), rng.uni(1.2, 1.8));
+  const double T = lm.scan_period;
+  const double sp = rng.uni(0, cfg->v_max);
+  Twist tw{T * V3D(0, 0, rng.uni(-cfg->w_max, cfg->w_max)), T * V3D(sp, 0.1 * sp, 0.0)};
+  Cloud raw;
+  simulate_scan(w, lm, T0, tw, cfg->range_noise, rng, raw);
+  const int n = (int)std::min<size_t>(raw.size(), (size_t)std::max(cap, 0));
+  std::memcpy(out, raw.points.data(), sizeof(lins_point) * (size_t)n);
+  return n;
+}
+
 }  // extern "C"
