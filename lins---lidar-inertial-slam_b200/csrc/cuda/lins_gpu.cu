@@ -32,7 +32,9 @@
 using namespace lins_dev;
 
 // lins_jacobian.cu
-extern "C" int lins_launch_jacobian_mma(const lins_dev::BatchView* bv, const lins_dev::KParams* kp, int n_units, int sm_count, cudaStream_t stream);
+extern "C" int lins_jacobian_parts(int n_units, int sm_count);
+extern "C" int lins_launch_jacobian_mma(const lins_dev::BatchView* bv, const lins_dev::KParams* kp, int n_units, int sm_count, int P, double* part_acc,
+                                        int* part_cnt, cudaStream_t stream);
 
 namespace {
 
@@ -534,6 +536,8 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
   int max_ts = 0, max_tc = 0;
   DevBuf<int> qs_off, qc_off, ts_off, tc_off, ind_s, ind_c, counter;
   DevBuf<long long> timers;
+  DevBuf<double> jac_part;         // split Jacobian kernel: per-(unit, part) sums and arrival counters
+  DevBuf<int> jac_cnt;
   DevBuf<IcpState> icp;            // pose-update state of the ICP fallback loop (lins_gpu_estimate_transform)
   PinBuf<IcpState> h_icp;
   DevBuf<double> state_in, cov_in, state_out, cov_out, accum;
@@ -552,7 +556,7 @@ struct Resident {  // one resident batch (device) + its pinned staging (host)
     state_out.release(); cov_out.release(); accum.release(); results.release(); reports.release(); sel_s.release();
     sel_c.release(); coeff_s.release(); coeff_c.release(); mask_s.release(); mask_c.release(); h_pts.release();
     h_off.release(); h_state.release(); h_cov.release(); h_state_out.release(); h_cov_out.release();
-    h_accum.release(); h_results.release(); h_reports.release(); icp.release(); h_icp.release();
+    h_accum.release(); h_results.release(); h_reports.release(); icp.release(); h_icp.release(); jac_part.release(); jac_cnt.release();
   }
 };
 
@@ -581,6 +585,7 @@ struct lins_ctx {
   DevBuf<float4> tmp_pts;
   DevBuf<lins_point> tmp_out;  // transformed clouds as full PointXYZI records (update_map read-back)
   cudaEvent_t tmp_ev = nullptr; // recorded after the last H2D copies that read h_tmp
+  PinBuf<lins_point> h_out;     // pinned staging of the update_map read-back
   DevBuf<double> tmp_lin;
   PinBuf<float4> h_tmp;
   // row F2 (scan-to-map refinement): the map clouds, the current feature clouds, search / reduction scratch
@@ -859,7 +864,7 @@ void lins_gpu_destroy(lins_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   ctx->batch.release(); ctx->single.release();
   ctx->map_s.release(); ctx->map_c.release(); ctx->tree_s.release(); ctx->tree_c.release(); ctx->map_off.release();
-  ctx->tmp_pts.release(); ctx->tmp_lin.release(); ctx->tmp_out.release(); ctx->h_tmp.release(); ctx->mp.release();
+  ctx->tmp_pts.release(); ctx->tmp_lin.release(); ctx->tmp_out.release(); ctx->h_out.release(); ctx->h_tmp.release(); ctx->mp.release();
   if (ctx->tmp_ev) cudaEventDestroy(ctx->tmp_ev);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -1376,7 +1381,9 @@ int lins_gpu_batch_jacobian_pass(lins_ctx* ctx, double* accum_out) {
     if (grid < 1) grid = 1;
     lins_jacobian_kernel<128, 5><<<grid, 128, 0, ctx->stream>>>(bv, kp);  // measured: 83 us per 5000 units (96 registers, 20 warps per SM)
   } else {
-    const int e = lins_launch_jacobian_mma(&bv, &kp, r.n, ctx->sm_count, ctx->stream);
+    const int P = lins_jacobian_parts(r.n, ctx->sm_count);
+    if (P > 1) { CK(r.jac_part.reserve((size_t)r.n * P * 32)); CK(r.jac_cnt.reserve((size_t)r.n)); }
+    const int e = lins_launch_jacobian_mma(&bv, &kp, r.n, ctx->sm_count, P, r.jac_part.p, r.jac_cnt.p, ctx->stream);
     if (e != 0) return fail(ctx, LINS_E_CUDA, "jacobian kernel launch", (cudaError_t)e);
   }
   CK(cudaGetLastError());
@@ -1555,10 +1562,13 @@ int lins_gpu_update_map_ex(lins_ctx* ctx, const lins_point* surf, int ns, const 
   if (map_replaced) *map_replaced = rebuild ? 1 : 0;
   int rc = upload_map_offsets(ctx);
   if (rc != LINS_OK) return rc;
-  if (want_out) {
-    if (o_s) CK(cudaMemcpyAsync(surf_out, o_s, sizeof(lins_point) * ns, cudaMemcpyDeviceToHost, ctx->stream));
-    if (o_c) CK(cudaMemcpyAsync(corner_out, o_c, sizeof(lins_point) * nc, cudaMemcpyDeviceToHost, ctx->stream));
+  if (want_out) {  // full records through pinned staging (a D2H into pageable memory is staged chunk by chunk by the driver)
+    CK(ctx->h_out.reserve((size_t)ns + nc + 1));
+    if (o_s) CK(cudaMemcpyAsync(ctx->h_out.p, o_s, sizeof(lins_point) * ns, cudaMemcpyDeviceToHost, ctx->stream));
+    if (o_c) CK(cudaMemcpyAsync(ctx->h_out.p + ns, o_c, sizeof(lins_point) * nc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (o_s) std::memcpy(surf_out, ctx->h_out.p, sizeof(lins_point) * ns);
+    if (o_c) std::memcpy(corner_out, ctx->h_out.p + ns, sizeof(lins_point) * nc);
   }
   return LINS_OK;
 }

@@ -16,6 +16,8 @@
 //   * one warp per unit in a two-deep software pipeline: while trip k is computed, the gathers of trip k + 1 and the
 //     query / ID loads of trip k + 2 are in flight (a unit's ~16 trips are a serial chain: its memory latency, not the
 //     SM's issue rate, is what one warp per unit has to hide).
+#include <cstdlib>
+
 #include "lins_kernels.cuh"
 
 namespace lins_dev {
@@ -38,15 +40,20 @@ __device__ __forceinline__ void sincos_small(double x, double& sn, double& cs) {
   cs = 1.0 + x2 * (-0.5 + x2 * (1.0 / 24 + x2 * (-1.0 / 720 + x2 * (1.0 / 40320 + x2 * (-1.0 / 3628800 + x2 * (1.0 / 479001600))))));
 }
 
+// P = parts a unit is cut into (trips dealt round-robin to P warps): with one warp per unit and only a few units per warp the
+// grid's last round is nearly empty; cutting units keeps every warp busy to the end.  The parts' sums meet in part_acc and
+// the warp that arrives last adds them in part order (deterministic).
 __global__ void __launch_bounds__(kJacWarps * 32, LINS_JAC_MIN_CTAS) lins_jacobian_mma_kernel(const __grid_constant__ BatchView bv,
-                                                                                             const __grid_constant__ KParams kp) {
+                                                                                             const __grid_constant__ KParams kp, int P,
+                                                                                             double* __restrict__ part_acc, int* __restrict__ part_cnt) {
   __shared__ __align__(16) double stage[kJacWarps][32 * kJacRow];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* my = stage[warp];
   const int warps_per_grid = gridDim.x * kJacWarps;
   const double inv_period = 1.f / kp.scan_period;
   const bool weighted = kp.iter0 >= kp.icp_freq;
-  for (int scan = blockIdx.x * kJacWarps + warp; scan < bv.n_scans; scan += warps_per_grid) {
+  for (int item = blockIdx.x * kJacWarps + warp; item < bv.n_scans * P; item += warps_per_grid) {
+    const int scan = item / P, part = item - scan * P;
     // per-unit constants (every lane computes the same values)
     const double* st = bv.state_in + (size_t)scan * 20;
     const double rn0 = st[0], rn1 = st[1], rn2 = st[2];
@@ -94,20 +101,21 @@ __global__ void __launch_bounds__(kJacWarps * 32, LINS_JAC_MIN_CTAS) lins_jacobi
     bool have;
     {
       int a1, a2, a3;
-      fetch(lane, pc, a1, a2, a3);
-      have = gather(lane, a1, a2, a3, t1, t2, t3);
-      fetch(lane + 32, pn, n1, n2, n3);
+      fetch(part * 32 + lane, pc, a1, a2, a3);
+      have = gather(part * 32 + lane, a1, a2, a3, t1, t2, t3);
+      fetch((part + P) * 32 + lane, pn, n1, n2, n3);
     }
-    for (int i0 = 0; i0 < ns + nc; i0 += 32) {
+    const int stride = 32 * P;
+    for (int i0 = part * 32; i0 < ns + nc; i0 += stride) {
       const int i = i0 + lane;
       const float4 p = pc;
       const bool surf = i < ns;
       const float4 u1 = t1, u2 = t2, u3 = t3;
       const bool chave = have;
       // next trip: its gathers now (IDs arrived during the previous trip); the trip after: its streaming loads
-      have = gather(i + 32, n1, n2, n3, t1, t2, t3);
+      have = gather(i + stride, n1, n2, n3, t1, t2, t3);
       pc = pn;
-      fetch(i + 64, pn, n1, n2, n3);
+      fetch(i + 2 * stride, pn, n1, n2, n3);
       double g[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, r = 0.0;
       bool ok = false;
       if (chave) {
@@ -149,6 +157,7 @@ __global__ void __launch_bounds__(kJacWarps * 32, LINS_JAC_MIN_CTAS) lins_jacobi
     }
     // C[i][j] with i = lane / 4, j = 2 * (lane % 4) + {0, 1}: upper triangle of the 6 x 6 block -> entries 0..20 (row-major),
     // column 6 -> g r (21..26) and r r (27)
+    double* dst = P == 1 ? bv.accum + (size_t)scan * 32 : part_acc + ((size_t)scan * P + part) * 32;
     const int ci = lane >> 2;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -158,28 +167,58 @@ __global__ void __launch_bounds__(kJacWarps * 32, LINS_JAC_MIN_CTAS) lins_jacobi
         int e;
         if (cj < 6) e = ci * 6 - (ci * (ci - 1)) / 2 + (cj - ci);
         else e = ci < 6 ? 21 + ci : 27;
-        bv.accum[(size_t)scan * 32 + e] = v;
+        dst[e] = v;
       }
     }
 #ifdef LINS_JAC_FOLD_SHUFFLE
     __syncwarp();
-    if (lane < kNAcc) bv.accum[(size_t)scan * 32 + lane] = shuffle_total;
+    if (lane < kNAcc) dst[lane] = shuffle_total;
 #endif
-    if (lane == 28) bv.accum[(size_t)scan * 32 + 28] = (double)cs;
-    if (lane == 29) bv.accum[(size_t)scan * 32 + 29] = (double)cc;
+    if (lane == 28) dst[28] = (double)cs;
+    if (lane == 29) dst[29] = (double)cc;
+    if (P > 1) {
+      __threadfence();
+      __syncwarp();
+      int old = 0;
+      if (lane == 0) old = atomicAdd(&part_cnt[scan], 1);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old == P - 1) {  // every part of this unit has arrived: add them in part order
+        __threadfence();
+        if (lane < 30) {
+          double v = 0.0;
+          for (int p = 0; p < P; ++p) v += __ldcg(part_acc + ((size_t)scan * P + p) * 32 + lane);
+          bv.accum[(size_t)scan * 32 + lane] = v;
+        }
+      }
+    }
   }
 }
 
 }  // namespace lins_dev
 
 // launched from lins_gpu.cu (lins_gpu_batch_jacobian_pass)
-extern "C" int lins_launch_jacobian_mma(const lins_dev::BatchView* bv, const lins_dev::KParams* kp, int n_units, int sm_count, cudaStream_t stream) {
+// parts per unit.  Measured on B200 (5000 units, 2368 resident warps): P = 1 68 us, 2 83 us, 3 86 us, 4 100 us — the kernel
+// is bound by its scattered 32-B sector gathers, not by the emptiness of the grid's last round, and cutting units only adds
+// per-unit set-up and spoils locality.  One part unless the batch cannot even fill the resident warps (LINS_JAC_PARTS: A/B).
+extern "C" int lins_jacobian_parts(int n_units, int sm_count) {
   using namespace lins_dev;
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lins_jacobian_mma_kernel, kJacWarps * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-  int grid = (n_units + kJacWarps - 1) / kJacWarps;
+  const long warps = (long)sm_count * per_sm * kJacWarps;
+  long P = n_units > 0 && n_units < warps / 2 ? warps / n_units : 1;
+  if (const char* e = std::getenv("LINS_JAC_PARTS")) P = std::atoi(e);
+  return (int)(P < 1 ? 1 : (P > 4 ? 4 : P));
+}
+extern "C" int lins_launch_jacobian_mma(const lins_dev::BatchView* bv, const lins_dev::KParams* kp, int n_units, int sm_count, int P, double* part_acc,
+                                        int* part_cnt, cudaStream_t stream) {
+  using namespace lins_dev;
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lins_jacobian_mma_kernel, kJacWarps * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  long items = (long)n_units * P;
+  int grid = (int)((items + kJacWarps - 1) / kJacWarps);
   if (grid > sm_count * per_sm) grid = sm_count * per_sm;
   if (grid < 1) grid = 1;
-  lins_jacobian_mma_kernel<<<grid, kJacWarps * 32, 0, stream>>>(*bv, *kp);
+  if (P > 1 && cudaMemsetAsync(part_cnt, 0, sizeof(int) * (size_t)n_units, stream) != cudaSuccess) return (int)cudaGetLastError();
+  lins_jacobian_mma_kernel<<<grid, kJacWarps * 32, 0, stream>>>(*bv, *kp, P, part_acc, part_cnt);
   return (int)cudaGetLastError();
 }
