@@ -349,6 +349,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     e2e_counts = [0] * NE
+    up0 = [c.batch_upload_stats() for c in e2e_ctxs]
 
     def e2e_worker(j):
         for k in range(j, e2e_steps, NE):
@@ -374,14 +375,16 @@ def main():
             capi.unpin_batch(b)
     b0 = batches[0]
     pts = sum(int(b0.offsets[k][-1]) for k in b0.FIELDS)
-    # the library's default policy: caller-pinned clouds are DMA'd raw (32 B / point, packed on the device) when a context has
-    # fewer than 8 host pack threads to itself, otherwise host threads pack them to 16 B / point into pinned staging
+    # caller-pinned clouds are split at run time between the pack threads (16 B / point over PCIe) and the copy engine (raw
+    # 32 B / point, packed on the device): count what actually went which way in the timed region
     pack_threads = int(os.environ.get("LINS_PACK_THREADS", "8"))
-    forced = os.environ.get("LINS_UPLOAD")
-    direct = e2e_pinned and (forced in ("direct", "pinned") or (forced is None and pack_threads < 8))
-    upload_mode = ("caller-pinned 32-B PointXYZI clouds: raw DMA + device pack (no host pass over the points)" if direct else
-                   f"32-B PointXYZI clouds packed to 16 B by {pack_threads} host threads per context into pinned staging")
-    h2d = (32 if direct else 16) * pts + 4 * 4 * (n + 1) + n * (20 + 324) * 8
+    up1 = [c.batch_upload_stats() for c in e2e_ctxs]
+    packed_pts = sum(b_[0] - a_[0] for a_, b_ in zip(up0, up1)); raw_pts = sum(b_[1] - a_[1] for a_, b_ in zip(up0, up1))
+    raw_frac = raw_pts / max(1, packed_pts + raw_pts)
+    upload_mode = (f"caller-pinned 32-B PointXYZI clouds: {100 * (1 - raw_frac):.0f} % of the points packed to 16 B by {pack_threads} host threads per context, "
+                   f"{100 * raw_frac:.0f} % DMA'd raw and packed on the device (LINS_UPLOAD={os.environ.get('LINS_UPLOAD', 'default')})") if e2e_pinned else \
+                  f"pageable 32-B PointXYZI clouds packed to 16 B by {pack_threads} host threads per context into pinned staging"
+    h2d = int((16 * packed_pts + 32 * raw_pts) / max(1, e2e_steps)) + 4 * 4 * (n + 1) + n * (20 + 324) * 8
     d2h = n * ((20 + 324) * 8 + 64)
 
     if rank != 0:

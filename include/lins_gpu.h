@@ -162,6 +162,9 @@ int lins_gpu_update_map_ex(lins_ctx* ctx, const lins_point* surf_less_flat, int 
    batch on the ctx stream (asynchronous). download: D2H of results + stream sync; any pointer may be NULL. */
 int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* batch);
 int lins_gpu_batch_run(lins_ctx* ctx);
+/* cumulative number of points lins_gpu_batch_upload moved as host-packed 16-B records / as raw 32-B records (caller-pinned
+   clouds are split between the pack threads and the copy engine at run time): what the PCIe byte count of a job is made of. */
+int lins_gpu_batch_upload_stats(lins_ctx* ctx, int64_t* packed_points, int64_t* raw_points);
 int lins_gpu_batch_download(lins_ctx* ctx, double* state_out /*n x 19*/, double* cov_out /*n x 324*/,
                             lins_scan_result* results /*n*/, lins_report* reports /*n, optional*/);
 /* The correspondence IDs the resident batch holds after a run — pointSearchSurfInd1/2/3 and pointSearchCornerInd1/2

@@ -29,6 +29,7 @@ EXPORTS = [
     "lins_gpu_batch_results_device", "lins_gpu_batch_jacobian_pass", "lins_gpu_launch_count", "lins_gpu_sync",
     "lins_gpu_debug_phase_cycles", "lins_gpu_map_set", "lins_gpu_scan2map", "lins_gpu_map_associate",
     "lins_gpu_host_register", "lins_gpu_host_unregister", "lins_gpu_batch_download_indices", "lins_gpu_update_map_ex",
+    "lins_gpu_batch_upload_stats",
 ]
 
 NVCC_COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
@@ -96,6 +97,8 @@ def lib():
         L.lins_gpu_map_associate.argtypes = [vp, vp, C.c_int, vp, C.c_int, vp] + [vp] * 6
         L.lins_gpu_host_register.argtypes = [vp, C.c_size_t]
         L.lins_gpu_batch_download_indices.argtypes = [vp, vp, vp]
+        if hasattr(L, "lins_gpu_batch_upload_stats"):
+            L.lins_gpu_batch_upload_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.lins_gpu_host_unregister.argtypes = [vp]
         _LIB = L
     return _LIB
@@ -260,6 +263,12 @@ class LinsGpu:
         self._keep = batch  # keep the host arrays alive while the async copies are in flight
         self._ck(self.L.lins_gpu_batch_upload(self.h, C.byref(d)))
         self._batch_n = batch.n
+
+    def batch_upload_stats(self):
+        """(points uploaded as host-packed 16-B records, points uploaded as raw 32-B records), cumulative."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.lins_gpu_batch_upload_stats(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def batch_run(self):
         self._ck(self.L.lins_gpu_batch_run(self.h))

@@ -572,6 +572,7 @@ struct lins_ctx {
   int sm_count = 148;
   int max_smem_optin = 0;
   int64_t launches = 0;
+  int64_t upload_raw_points = 0, upload_packed_points = 0;  // cumulative split of lins_gpu_batch_upload (raw DMA vs host pack)
   Resident batch;   // lins_gpu_batch_* working set
   Resident single;  // lins_gpu_ieskf / associate / estimate_transform (n = 1)
   // the single-scan map: "last" clouds (walks + tripods) and the clouds the 1-NN index was built on
@@ -988,12 +989,13 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
   size_t seg[5] = {0, r.nqs, r.nqs + r.nqc, r.nqs + r.nqc + r.nts, total};
   float4* dsts[4] = {r.qs.p, r.qc.p, r.ts.p, r.tc.p};
   int* doffs[4] = {r.qs_off.p, r.qc_off.p, r.ts_off.p, r.tc_off.p};
-  // Clouds in caller-PINNED host memory (cudaHostAlloc / cudaHostRegister): the copy engine reads the raw 32-B records
-  // straight from the caller's buffer and a device kernel packs them — no host pass over the points at all (twice the
-  // PCIe bytes, zero host memory traffic besides the DMA reads; what makes a many-GPU host scale).  LINS_UPLOAD=pack
-  // forces the host-pack path, LINS_UPLOAD=direct the DMA path for every pinned cloud, LINS_UPLOAD=pinned additionally
-  // fails the call when a cloud is not pinned.
-  bool direct[4] = {false, false, false, false};
+  // Clouds in caller-PINNED host memory (cudaHostAlloc / cudaHostRegister) can also go the other way: the copy engine reads
+  // the raw 32-B records straight from the caller's buffer and a device kernel packs them — twice the PCIe bytes, but no host
+  // pass over the points.  The clouds are cut into 64 K-point slices; pack threads take slices from the front of the list
+  // (pack -> pinned staging -> 16-B H2D), a feeder hands slices from the back to the copy engine as raw records.
+  // LINS_UPLOAD=pack: host pack only; =direct: raw DMA for every pinned cloud; =pinned: as direct, and an unpinned cloud
+  // fails the call; =hybrid: both ends at once, the feeder never more than two slices ahead (kept for experiments: it did
+  // not beat the better of the two pure modes).
   // pack threads: LINS_PACK_THREADS when set (a job that runs several contexts / ranks per host divides the cores
   // among them), else half the hardware threads, at most 32
   int want_threads;
@@ -1002,57 +1004,88 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
     want_threads = (int)std::min<unsigned>(hw ? hw / 2 : 4, 32);
     if (const char* e = std::getenv("LINS_PACK_THREADS")) { const int v = std::atoi(e); if (v >= 1) want_threads = std::min(v, 64); }
   }
-  {
-    // default policy: with plenty of host threads per context the host pack wins (half the PCIe bytes); with few — many
-    // contexts / ranks sharing one host — the raw DMA does (no host memory traffic beyond the DMA reads)
-    const char* mode = std::getenv("LINS_UPLOAD");
-    const bool force_pack = (mode && std::strcmp(mode, "pack") == 0) || (!mode && want_threads >= 8);
-    for (int k = 0; k < 4 && !force_pack; ++k) {
-      if (seg[k + 1] == seg[k]) continue;
-      cudaPointerAttributes at;
-      if (cudaPointerGetAttributes(&at, pts[k]) == cudaSuccess && at.type == cudaMemoryTypeHost) direct[k] = true;
-      else cudaGetLastError();
-      if (!direct[k] && mode && std::strcmp(mode, "pinned") == 0) return fail(ctx, LINS_E_INVALID, "LINS_UPLOAD=pinned but a cloud is not in pinned host memory");
-    }
-    if (direct[0] || direct[1] || direct[2] || direct[3]) CK(r.raw.reserve(2 * total + 2));
-    for (int k = 0; k < 4; ++k) {
-      if (!direct[k]) continue;
-      const size_t cnt = seg[k + 1] - seg[k];
-      float4* rawk = r.raw.p + 2 * seg[k];
-      CK(cudaMemcpyAsync(rawk, pts[k], sizeof(lins_point) * cnt, cudaMemcpyHostToDevice, ctx->stream));
-      const int blocks = (int)std::min<size_t>((cnt + 255) / 256, (size_t)ctx->sm_count * 8);
-      lins_pack_points_kernel<<<blocks, 256, 0, ctx->stream>>>(rawk, dsts[k], cnt);
-      CK(cudaGetLastError());
-      ctx->launches += 1;
-    }
+  const char* mode = std::getenv("LINS_UPLOAD");
+  // default: host pack when this context has >= 8 pack threads to itself (measured, 2 GPUs x 3 contexts: 10 threads each
+  // 6.1 M it/s per GPU; raw DMA 3.8 M whatever the threads; the two-ended split with 2-5 threads 3.3-3.6 M), raw DMA otherwise
+  const bool mode_pack = mode ? std::strcmp(mode, "pack") == 0 : want_threads >= 8;
+  const bool mode_direct = mode ? (std::strcmp(mode, "direct") == 0 || std::strcmp(mode, "pinned") == 0) : want_threads < 8;
+  bool pinned[4] = {false, false, false, false};
+  bool any_pinned = false;
+  for (int k = 0; k < 4 && !mode_pack; ++k) {
+    if (seg[k + 1] == seg[k]) continue;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, pts[k]) == cudaSuccess && at.type == cudaMemoryTypeHost) { pinned[k] = true; any_pinned = true; }
+    else cudaGetLastError();
+    if (!pinned[k] && mode && std::strcmp(mode, "pinned") == 0) return fail(ctx, LINS_E_INVALID, "LINS_UPLOAD=pinned but a cloud is not in pinned host memory");
   }
+  if (any_pinned) CK(r.raw.reserve(2 * total + 2));
   {
     struct Slice { int k; size_t a, b; };
-    std::vector<Slice> slices;
+    std::vector<Slice> slices;  // unpinned clouds first: only the pack threads may take those
     const size_t SL = 1u << 16;
-    for (int k = 0; k < 4; ++k) {
-      if (direct[k]) continue;
-      for (size_t a = 0; a < seg[k + 1] - seg[k]; a += SL) slices.push_back(Slice{k, a, std::min(a + SL, seg[k + 1] - seg[k])});
-    }
-    std::atomic<size_t> next(0);
+    size_t n_unpinned = 0;
+    for (int pass = 0; pass < 2; ++pass)
+      for (int k = 0; k < 4; ++k) {
+        if ((pass == 0) == pinned[k]) continue;
+        for (size_t a = 0; a < seg[k + 1] - seg[k]; a += SL) slices.push_back(Slice{k, a, std::min(a + SL, seg[k + 1] - seg[k])});
+        if (pass == 0) n_unpinned = slices.size();
+      }
+    // one list, two ends: lo = next slice for the pack threads, hi = one past the last slice not yet taken by the DMA feeder
+    std::mutex mu;
+    size_t lo = 0, hi = slices.size();
     std::atomic<int> cuda_err(0);
     const int device = ctx->device;
     cudaStream_t stream = ctx->stream;
+    auto take_front = [&](size_t& i) { std::lock_guard<std::mutex> g(mu); if (lo >= hi) return false; i = lo++; return true; };
+    auto take_back = [&](size_t& i) { std::lock_guard<std::mutex> g(mu); if (lo >= hi || hi - 1 < n_unpinned) return false; i = --hi; return true; };
     auto worker = [&]() {
       cudaSetDevice(device);
-      for (;;) {
-        size_t i = next.fetch_add(1);
-        if (i >= slices.size()) break;
+      size_t i;
+      while (take_front(i)) {
         const Slice& sl = slices[i];
         pack_into(hp + seg[sl.k] + sl.a, pts[sl.k] + sl.a, (int)(sl.b - sl.a));
         cudaError_t e = cudaMemcpyAsync(dsts[sl.k] + sl.a, hp + seg[sl.k] + sl.a, sizeof(float4) * (sl.b - sl.a), cudaMemcpyHostToDevice, stream);
         if (e != cudaSuccess) cuda_err.store((int)e);
       }
     };
-    int nthr = (int)std::min<size_t>((size_t)want_threads, std::max<size_t>(slices.size(), 1));
-    if (nthr < 1) nthr = 1;
-    if (!slices.empty()) ctx->pool.run(nthr, worker);
-    if (cuda_err.load() != 0) return fail(ctx, LINS_E_CUDA, "H2D copy of a packed slice", (cudaError_t)cuda_err.load());
+    const bool feed_raw = any_pinned && !mode_pack;
+    int nthr = mode_direct && n_unpinned == 0 ? 0 : (int)std::min<size_t>((size_t)want_threads, std::max<size_t>(slices.size(), 1));
+    // the DMA feeder (this thread): raw slices from the back, at most two in flight (all of them at once with LINS_UPLOAD=direct)
+    auto feeder = [&]() {
+      if (!feed_raw) return;
+      cudaEvent_t ev[2] = {nullptr, nullptr};
+      if (!mode_direct) for (auto& e : ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cuda_err.store((int)cudaGetLastError()); return; }
+      size_t i;
+      int turn = 0;
+      while (take_back(i)) {
+        const Slice& sl = slices[i];
+        const size_t cnt = sl.b - sl.a;
+        float4* rawk = r.raw.p + 2 * (seg[sl.k] + sl.a);
+        if (!mode_direct) cudaEventSynchronize(ev[turn]);  // (a never-recorded event is complete)
+        cudaError_t e = cudaMemcpyAsync(rawk, pts[sl.k] + sl.a, sizeof(lins_point) * cnt, cudaMemcpyHostToDevice, stream);
+        const int blocks = (int)std::min<size_t>((cnt + 255) / 256, (size_t)ctx->sm_count * 4);
+        lins_pack_points_kernel<<<blocks, 256, 0, stream>>>(rawk, dsts[sl.k] + sl.a, cnt);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) { cuda_err.store((int)e); break; }
+        ctx->launches += 1;
+        if (!mode_direct) { cudaEventRecord(ev[turn], stream); turn ^= 1; }
+      }
+      for (auto& e : ev) if (e) cudaEventDestroy(e);
+    };
+    if (nthr >= 1 && !slices.empty()) {
+      // the pool runs the workers; the calling thread feeds the copy engine meanwhile (HostPool::run blocks, so the feeder is
+      // the pool's first worker's prologue when only one thread is available)
+      std::atomic<int> first(0);
+      ctx->pool.run(nthr + (feed_raw ? 1 : 0), [&]() { if (feed_raw && first.fetch_add(1) == 0) { cudaSetDevice(device); feeder(); } else worker(); });
+    } else {
+      feeder();
+    }
+    if (cuda_err.load() != 0) return fail(ctx, LINS_E_CUDA, "H2D copy of a slice", (cudaError_t)cuda_err.load());
+    // what went which way (lins_gpu_batch_upload_stats): slices [n_unpinned.., lo) were packed by the host, [hi, end) went raw
+    size_t raw_pts = 0;
+    for (size_t i = hi; i < slices.size(); ++i) raw_pts += slices[i].b - slices[i].a;
+    ctx->upload_raw_points += (int64_t)raw_pts;
+    ctx->upload_packed_points += (int64_t)(total - raw_pts);
   }
   for (int k = 0; k < 4; ++k) std::memcpy(r.h_off.p + (size_t)k * (n + 1), offs[k], sizeof(int) * (n + 1));
   for (int i = 0; i < n; ++i) {
@@ -1065,6 +1098,13 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
   CK(cudaMemcpyAsync(r.state_in.p, r.h_state.p, sizeof(double) * 20 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(r.cov_in.p, r.h_cov.p, sizeof(double) * 324 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   return reserve_outputs(ctx, r, true, false);
+}
+
+int lins_gpu_batch_upload_stats(lins_ctx* ctx, int64_t* packed_points, int64_t* raw_points) {
+  if (!ctx) return LINS_E_INVALID;
+  if (packed_points) *packed_points = ctx->upload_packed_points;
+  if (raw_points) *raw_points = ctx->upload_raw_points;
+  return LINS_OK;
 }
 
 int lins_gpu_batch_run(lins_ctx* ctx) {

@@ -264,3 +264,45 @@ def test_bag_replay_equals_direct_drive(gpu, ob, synth, tmp_path):
     units = replay["units"]
     so, co, ro, _, _ = ob.ieskf_batch(ob.LinsParams.shipped(), units, threads=2)
     assert np.array_equal(replay["iters"], ro["iters"]) and np.abs(replay["state_out"] - so).max() <= 1e-7
+
+
+def test_pinned_direct_upload_equals_host_pack(gpu, capi, synth):
+    """lins_gpu_batch_upload with caller-pinned clouds (lins_gpu_host_register) and the raw-DMA + device-pack path
+    (LINS_UPLOAD=direct; the default policy picks it when few host threads per context are available, i.e. many ranks on
+    one host) must give bit-identical results to the host-pack path, also for ragged / empty clouds."""
+    b = synth.generate("config3", n=24, seed0=777)
+    s0, c0, r0 = gpu.ieskf_batch(b)
+    old = os.environ.get("LINS_UPLOAD")
+    try:
+        capi.pin_batch(b)
+        os.environ["LINS_UPLOAD"] = "pinned"  # fails the call if a cloud is not pinned
+        s1, c1, r1 = gpu.ieskf_batch(b)
+        os.environ["LINS_UPLOAD"] = "pack"
+        s2, c2, r2 = gpu.ieskf_batch(b)
+        os.environ["LINS_UPLOAD"] = "hybrid"  # pack threads and the copy engine share the slices
+        os.environ["LINS_PACK_THREADS"] = "1"
+        big = synth.generate("config3", n=64, seed0=800)  # several 64 K-point slices per cloud
+        sb0, cb0, _ = gpu.ieskf_batch(big)
+        capi.pin_batch(big)
+        p0 = gpu.batch_upload_stats()
+        sb1, cb1, _ = gpu.ieskf_batch(big)
+        p1 = gpu.batch_upload_stats()
+        capi.unpin_batch(big)
+        assert np.array_equal(sb0, sb1) and np.array_equal(cb0, cb1)
+        assert (p1[0] - p0[0]) + (p1[1] - p0[1]) == sum(int(big.offsets[k][-1]) for k in big.FIELDS) and p1[1] > p0[1]
+    finally:
+        os.environ.pop("LINS_PACK_THREADS", None)
+        capi.unpin_batch(b)
+        if old is None:
+            os.environ.pop("LINS_UPLOAD", None)
+        else:
+            os.environ["LINS_UPLOAD"] = old
+    assert np.array_equal(s0, s1) and np.array_equal(c0, c1) and np.array_equal(r0["iters"], r1["iters"])
+    assert np.array_equal(s0, s2) and np.array_equal(c0, c2)
+    # an unpinned cloud under LINS_UPLOAD=pinned is an error, not a silent fallback
+    os.environ["LINS_UPLOAD"] = "pinned"
+    try:
+        with pytest.raises(capi.LinsError):
+            gpu.ieskf_batch(synth.generate("config3", n=2, seed0=778))
+    finally:
+        os.environ.pop("LINS_UPLOAD", None)
