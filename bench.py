@@ -66,6 +66,30 @@ def host_info():
     return {"nproc": os.cpu_count() or 1, "cpu_model": model}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank (and every thread it starts: the generator's, the library's pack pool) to the CPUs of the NUMA node its
+    GPU hangs off, so that the host clouds — first touched by these threads — and the pinned staging are node-local to the
+    GPU's PCIe root.  What a replay job with one rank per GPU does; returns a description for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return f"{bdf}: no NUMA affinity reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"{bdf}: node {node} has no allowed CPUs"
+        os.sched_setaffinity(0, cpus)
+        return f"GPU {local} ({bdf}) -> NUMA node {node}, {len(cpus)} CPUs"
+    except (OSError, ValueError, AttributeError) as e:
+        return f"not bound ({type(e).__name__})"
+
+
 def thread_sweep(cores):
     return sorted({max(1, cores // 4), max(1, cores // 2), cores})
 
@@ -231,6 +255,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi, synth, defs = pkg("capi"), pkg("synth"), pkg("ctypes_defs")
     prm = defs.LinsParams.shipped()
+    # (opt-in: measured on the 2-socket B200 host it LOWERED the 2-GPU e2e — 12.2 -> 9.8 M it/s with host pack, 7.7 -> 6.1 M
+    # with raw DMA — because it halves the CPUs the rank's pack threads and copy threads may use)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("LINS_NUMA_BIND", "0") == "1" else "not bound"
     # host threads each lins_gpu_batch_upload may use for packing: the cores are shared by `world` ranks x 3 contexts
     os.environ.setdefault("LINS_PACK_THREADS", str(max(2, min(32, (os.cpu_count() or 8) // (max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))) * 6)))))
     # a non-default torch stream: its handle is non-NULL, so the library launches on it (NULL would make the
@@ -571,7 +598,7 @@ def main():
         "iterations_per_step_rank0": float(np.mean(iters_per_batch)),
         "streams": f"one CUDA stream per resident batch ({NB}): consecutive steps overlap at their kernel tails; e2e = {NE} host threads, one context (and stream) each",
         "clocks": clk,
-        "e2e": {"value": e2e_iters / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "host_threads": NE,
+        "e2e": {"value": e2e_iters / e2e_s, "unit": "iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "host_threads": NE, "numa": numa,
                 "upload": upload_mode},
         "gpu_launches": int(total_launches),
         "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_jacobian": roofline_j, "mapping_refinement": mapping,
