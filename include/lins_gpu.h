@@ -101,7 +101,13 @@ typedef struct lins_batch_desc {
   const lins_point* corner_less_sharp; const int32_t* corner_less_sharp_off; /* targets: last cornerPointsLessSharp_ */
   const double* state_in;              /* n_scans x 19 : filter_->state_ */
   const double* cov_in;                /* n_scans x 324: filter_->covariance_ */
+  int32_t point_format;                /* LINS_POINTS_XYZI32 (0, default): the four clouds are pcl::PointXYZI records as typed
+                                          above; LINS_POINTS_PACKED16: they are 16-byte (x, y, z, intensity) float records (cast
+                                          the pointers) — what the device keeps anyway, so a caller that stores its clouds this
+                                          way (and page-locks them) uploads with no host pass and half the PCIe bytes */
 } lins_batch_desc;
+#define LINS_POINTS_XYZI32 0
+#define LINS_POINTS_PACKED16 1
 
 typedef struct lins_ctx lins_ctx;
 

@@ -108,7 +108,7 @@ class LinsError(RuntimeError):
     pass
 
 
-def pin_batch(batch: Batch):
+def pin_batch(batch):
     """Page-lock the four cloud arrays of a host batch in place (lins_gpu_host_register): lins_gpu_batch_upload then DMAs
     the raw records straight from them.  Returns the list of pinned arrays; call unpin_batch before they are freed."""
     L = lib()
@@ -132,7 +132,7 @@ def unpin_arrays(arrays):
         L.lins_gpu_host_unregister(a.ctypes.data)
 
 
-def unpin_batch(batch: Batch):
+def unpin_batch(batch):
     unpin_arrays(getattr(batch, "_pinned", []))
     batch._pinned = []
 
@@ -258,7 +258,7 @@ class LinsGpu:
         return out
 
     # ---- batched mode ------------------------------------------------------------------------------------------
-    def batch_upload(self, batch: Batch):
+    def batch_upload(self, batch):
         d = batch.desc()
         self._keep = batch  # keep the host arrays alive while the async copies are in flight
         self._ck(self.L.lins_gpu_batch_upload(self.h, C.byref(d)))
@@ -289,7 +289,7 @@ class LinsGpu:
         self._ck(self.L.lins_gpu_batch_download_indices(self.h, ptr(si), ptr(ci)))
         return si, ci
 
-    def ieskf_batch(self, batch: Batch, covs=True):
+    def ieskf_batch(self, batch, covs=True):
         """upload + run + download through host buffers: the end-to-end entry point."""
         d = batch.desc()
         n = batch.n

@@ -969,6 +969,8 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
     if (offs[k][n] > 0 && !pts[k]) return fail(ctx, LINS_E_INVALID, "null cloud");
   }
   if (!b->state_in || !b->cov_in) return fail(ctx, LINS_E_INVALID, "null prior");
+  if (b->point_format != LINS_POINTS_XYZI32 && b->point_format != LINS_POINTS_PACKED16) return fail(ctx, LINS_E_INVALID, "bad point_format");
+  const bool packed16 = b->point_format == LINS_POINTS_PACKED16;  // the clouds are already (x, y, z, intensity) float4 records
   r.nqs = offs[0][n]; r.nqc = offs[1][n]; r.nts = offs[2][n]; r.ntc = offs[3][n];
   r.max_q = 0; r.max_ts = 0; r.max_tc = 0;
   for (int i = 0; i < n; ++i) {
@@ -1007,8 +1009,9 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
   const char* mode = std::getenv("LINS_UPLOAD");
   // default: host pack when this context has >= 8 pack threads to itself (measured, 2 GPUs x 3 contexts: 10 threads each
   // 6.1 M it/s per GPU; raw DMA 3.8 M whatever the threads; the two-ended split with 2-5 threads 3.3-3.6 M), raw DMA otherwise
-  const bool mode_pack = mode ? std::strcmp(mode, "pack") == 0 : want_threads >= 8;
-  const bool mode_direct = mode ? (std::strcmp(mode, "direct") == 0 || std::strcmp(mode, "pinned") == 0) : want_threads < 8;
+  const bool p16 = b->point_format == LINS_POINTS_PACKED16;  // (16-B records from pinned memory: always straight DMA)
+  const bool mode_pack = mode ? std::strcmp(mode, "pack") == 0 : (want_threads >= 8 && !p16);
+  const bool mode_direct = mode ? (std::strcmp(mode, "direct") == 0 || std::strcmp(mode, "pinned") == 0) : (want_threads < 8 || p16);
   bool pinned[4] = {false, false, false, false};
   bool any_pinned = false;
   for (int k = 0; k < 4 && !mode_pack; ++k) {
@@ -1018,7 +1021,7 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
     else cudaGetLastError();
     if (!pinned[k] && mode && std::strcmp(mode, "pinned") == 0) return fail(ctx, LINS_E_INVALID, "LINS_UPLOAD=pinned but a cloud is not in pinned host memory");
   }
-  if (any_pinned) CK(r.raw.reserve(2 * total + 2));
+  if (any_pinned && !packed16) CK(r.raw.reserve(2 * total + 2));
   {
     struct Slice { int k; size_t a, b; };
     std::vector<Slice> slices;  // unpinned clouds first: only the pack threads may take those
@@ -1043,7 +1046,8 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
       size_t i;
       while (take_front(i)) {
         const Slice& sl = slices[i];
-        pack_into(hp + seg[sl.k] + sl.a, pts[sl.k] + sl.a, (int)(sl.b - sl.a));
+        if (packed16) std::memcpy(hp + seg[sl.k] + sl.a, reinterpret_cast<const float4*>(pts[sl.k]) + sl.a, sizeof(float4) * (sl.b - sl.a));
+        else pack_into(hp + seg[sl.k] + sl.a, pts[sl.k] + sl.a, (int)(sl.b - sl.a));
         cudaError_t e = cudaMemcpyAsync(dsts[sl.k] + sl.a, hp + seg[sl.k] + sl.a, sizeof(float4) * (sl.b - sl.a), cudaMemcpyHostToDevice, stream);
         if (e != cudaSuccess) cuda_err.store((int)e);
       }
@@ -1060,14 +1064,19 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
       while (take_back(i)) {
         const Slice& sl = slices[i];
         const size_t cnt = sl.b - sl.a;
-        float4* rawk = r.raw.p + 2 * (seg[sl.k] + sl.a);
         if (!mode_direct) cudaEventSynchronize(ev[turn]);  // (a never-recorded event is complete)
-        cudaError_t e = cudaMemcpyAsync(rawk, pts[sl.k] + sl.a, sizeof(lins_point) * cnt, cudaMemcpyHostToDevice, stream);
-        const int blocks = (int)std::min<size_t>((cnt + 255) / 256, (size_t)ctx->sm_count * 4);
-        lins_pack_points_kernel<<<blocks, 256, 0, stream>>>(rawk, dsts[sl.k] + sl.a, cnt);
-        if (e == cudaSuccess) e = cudaGetLastError();
+        cudaError_t e;
+        if (packed16) {  // already in the device's format: one DMA, nothing else
+          e = cudaMemcpyAsync(dsts[sl.k] + sl.a, reinterpret_cast<const float4*>(pts[sl.k]) + sl.a, sizeof(float4) * cnt, cudaMemcpyHostToDevice, stream);
+        } else {
+          float4* rawk = r.raw.p + 2 * (seg[sl.k] + sl.a);
+          e = cudaMemcpyAsync(rawk, pts[sl.k] + sl.a, sizeof(lins_point) * cnt, cudaMemcpyHostToDevice, stream);
+          const int blocks = (int)std::min<size_t>((cnt + 255) / 256, (size_t)ctx->sm_count * 4);
+          lins_pack_points_kernel<<<blocks, 256, 0, stream>>>(rawk, dsts[sl.k] + sl.a, cnt);
+          if (e == cudaSuccess) e = cudaGetLastError();
+          if (e == cudaSuccess) ctx->launches += 1;
+        }
         if (e != cudaSuccess) { cuda_err.store((int)e); break; }
-        ctx->launches += 1;
         if (!mode_direct) { cudaEventRecord(ev[turn], stream); turn ^= 1; }
       }
       for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -1084,6 +1093,7 @@ int lins_gpu_batch_upload(lins_ctx* ctx, const lins_batch_desc* b) {
     // what went which way (lins_gpu_batch_upload_stats): slices [n_unpinned.., lo) were packed by the host, [hi, end) went raw
     size_t raw_pts = 0;
     for (size_t i = hi; i < slices.size(); ++i) raw_pts += slices[i].b - slices[i].a;
+    if (packed16) raw_pts = 0;  // (16-B records either way)
     ctx->upload_raw_points += (int64_t)raw_pts;
     ctx->upload_packed_points += (int64_t)(total - raw_pts);
   }

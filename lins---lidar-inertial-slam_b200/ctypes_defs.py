@@ -88,6 +88,7 @@ class LinsBatchDesc(C.Structure):
         ("corner_less_sharp_off", C.c_void_p),
         ("state_in", C.c_void_p),
         ("cov_in", C.c_void_p),
+        ("point_format", C.c_int32),  # 0 = 32-B PointXYZI records, 1 = packed 16-B (x, y, z, intensity)
     ]
 
 
@@ -142,6 +143,10 @@ class Batch:
         d.cov_in = self.cov.ctypes.data
         return d
 
+    def packed16(self):
+        """The same batch with its clouds as packed (x, y, z, intensity) float32 records (lins_batch_desc.point_format = 1)."""
+        return PackedBatch(self)
+
     def unit(self, i):
         """The four clouds + prior of unit i."""
         out = {}
@@ -188,3 +193,27 @@ class Batch:
         clouds = {k: make_points(z[k][:, :3], z[k][:, 3]) for k in cls.FIELDS}
         offsets = {k: z[k + "_off"] for k in cls.FIELDS}
         return cls(clouds, offsets, z["state"], z["cov"], z["truth"] if "truth" in z.files else None)
+
+
+class PackedBatch:
+    """A Batch whose clouds are stored as 16-byte (x, y, z, intensity) records: LINS_POINTS_PACKED16."""
+
+    FIELDS = Batch.FIELDS
+
+    def __init__(self, batch):
+        self.n, self.offsets, self.state, self.cov = batch.n, batch.offsets, batch.state, batch.cov
+        self.clouds = {}
+        for k in self.FIELDS:
+            c = batch.clouds[k]
+            self.clouds[k] = np.ascontiguousarray(np.stack([c["x"], c["y"], c["z"], c["intensity"]], 1).astype(np.float32)) if len(c) else np.zeros((0, 4), np.float32)
+
+    def desc(self):
+        d = LinsBatchDesc()
+        d.n_scans = self.n
+        for k in self.FIELDS:
+            setattr(d, k, self.clouds[k].ctypes.data)
+            setattr(d, k + "_off", self.offsets[k].ctypes.data)
+        d.state_in = self.state.ctypes.data
+        d.cov_in = self.cov.ctypes.data
+        d.point_format = 1
+        return d

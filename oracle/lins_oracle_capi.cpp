@@ -154,6 +154,7 @@ int lins_oracle_nn(void* hv, int which, const float* xyz, int n, int use_kdtree,
 int lins_oracle_ieskf_batch(const lins_params* p, const lins_batch_desc* b, int first, int count, int form,
                             int use_kdtree, int n_threads, double* state_out, double* cov_out,
                             lins_scan_result* results, double* seconds_out, int64_t* iters_out) {
+  if (b->point_format != LINS_POINTS_XYZI32) return -1;  // the oracle reads pcl::PointXYZI records only
   if (n_threads < 1) n_threads = 1;
   std::atomic<int> next(0);
   std::atomic<long long> total_iters(0);

@@ -32,7 +32,7 @@ def test_struct_layouts_match_header(defs):
     assert defs.POINT_DTYPE.fields["intensity"][1] == 16  # pcl::PointXYZI: intensity at byte 16
     assert C.sizeof(defs.LinsParams) == 48
     assert C.sizeof(defs.LinsReport) == 16 + 64 * 4 * 2 + 64 * 8 * 2
-    assert C.sizeof(defs.LinsBatchDesc) == 8 + 10 * 8
+    assert C.sizeof(defs.LinsBatchDesc) == 8 + 10 * 8 + 8  # (+ point_format, padded)
     assert C.sizeof(defs.LinsMapReport) == 4 * 4 + 3 * 10 * 4  # row F2
     # the C side agrees (compile the header with gcc and print the sizes)
     import subprocess, tempfile

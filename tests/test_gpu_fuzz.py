@@ -306,3 +306,19 @@ def test_pinned_direct_upload_equals_host_pack(gpu, capi, synth):
             gpu.ieskf_batch(synth.generate("config3", n=2, seed0=778))
     finally:
         os.environ.pop("LINS_UPLOAD", None)
+
+
+def test_packed16_batch_equals_xyzi32(gpu, capi, synth):
+    """lins_batch_desc.point_format = LINS_POINTS_PACKED16: clouds handed over as 16-byte (x, y, z, intensity) records
+    (pageable -> staged by memcpy; pinned -> one DMA per slice, no pack kernel) give bit-identical results."""
+    b = synth.generate("config3", n=40, seed0=901)
+    s0, c0, r0 = gpu.ieskf_batch(b)
+    p = b.packed16()
+    s1, c1, r1 = gpu.ieskf_batch(p)
+    capi.pin_batch(p)
+    try:
+        s2, c2, r2 = gpu.ieskf_batch(p)
+    finally:
+        capi.unpin_batch(p)
+    for s_, c_, r_ in ((s1, c1, r1), (s2, c2, r2)):
+        assert np.array_equal(s0, s_) and np.array_equal(c0, c_) and np.array_equal(r0["iters"], r_["iters"])

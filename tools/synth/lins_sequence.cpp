@@ -295,6 +295,7 @@ void lins_seq_desc(void* h, lins_batch_desc* d) {
   d->surf_less_flat = r->surfLessFlat.data(); d->surf_less_flat_off = r->offSL.data();
   d->corner_less_sharp = r->cornerLessSharp.data(); d->corner_less_sharp_off = r->offCL.data();
   d->state_in = r->state_in.data(); d->cov_in = r->cov_in.data();
+  d->point_format = LINS_POINTS_XYZI32;
 }
 const double* lins_seq_array(void* h, int which) {
   SeqRecord* r = static_cast<SeqRecord*>(h);

@@ -339,6 +339,7 @@ void lins_synth_batch_desc(void* h, lins_batch_desc* d) {
   d->surf_less_flat = b->surfLessFlat.data(); d->surf_less_flat_off = b->surfLessFlatOff.data();
   d->corner_less_sharp = b->cornerLessSharp.data(); d->corner_less_sharp_off = b->cornerLessSharpOff.data();
   d->state_in = b->state.data(); d->cov_in = b->cov.data();
+  d->point_format = LINS_POINTS_XYZI32;
 }
 const double* lins_synth_batch_truth(void* h) { return static_cast<SynthBatch*>(h)->truth.data(); }
 // scan B's own less-* clouds (distorted frame): which = 0 surf, 1 corner
