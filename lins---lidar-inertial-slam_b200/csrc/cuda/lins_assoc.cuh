@@ -54,8 +54,8 @@ struct PassBuffers {           // per-query arrays, indexed by v = slot * qtile 
 
 __device__ __forceinline__ AzIndex az_index_of(const Smem& sm, const BatchView& bv, bool surf) {
   AzIndex ix;
-  if (surf) { ix.pts = bv.az_s + sm.ts0; ix.bstart = sm.azTabS; ix.nb = sm.nbS; ix.nrings = sm.nringsS; ix.T = sm.Ts; }
-  else { ix.pts = bv.az_c + sm.tc0; ix.bstart = sm.azTabC; ix.nb = sm.nbC; ix.nrings = sm.nringsC; ix.T = sm.Tc; }
+  if (surf) { ix.pts = bv.az_s + sm.ts0; ix.bstart = sm.azTabS; ix.elev = sm.elevS; ix.nb = sm.nbS; ix.nrings = sm.nringsS; ix.T = sm.Ts; }
+  else { ix.pts = bv.az_c + sm.tc0; ix.bstart = sm.azTabC; ix.elev = sm.elevC; ix.nb = sm.nbC; ix.nrings = sm.nringsC; ix.T = sm.Tc; }
   return ix;
 }
 
@@ -163,8 +163,9 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       const AzIndex ix = az_index_of(sm, bv, i < sm.ns);
       const float4 s = pb.sel[v];
       const int w1 = pb.qw[v].x;
-      const Top3 top = az_scan_nn_group<G>(ix, s, w1, sub, gmask);
-      if (sub == 0) nn_finish(v, ix, s, top, w1, pb.qa[v].w);
+      const float4 qag = pb.qa[v];
+      const Top3 top = az_scan_nn_group<G>(ix, s, w1, qag.z, qag.w, sub, gmask);
+      if (sub == 0) nn_finish(v, ix, s, top, w1, qag.w);
     }
     // P2: warps pull queries from the work list (the per-query cost is heavy-tailed; a static split leaves warps idle)
     for (;;) {
@@ -185,13 +186,13 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       if (w1 >= 0) {
         const int wp = sm.first_pass ? az_probe_window(ix, qa, w1) : -1;
         if (wp >= 0) {  // wide window (no usable previous answer): probe first, then search inside the implied window
-          const Top3 pr = az_scan_nn(ix, s, wp);
+          const Top3 pr = az_scan_nn(ix, s, wp, qa.z, sqrtf(widen(kProbeSq)));  // (a probe needs no exactness: anything it finds is an upper bound)
           if (pr.p1 >= 0) {
             w1 = az_nn_window(ix, az_seed_bound(ix, s, pr.p1, nearf), qa);
             if (lane == 0) pb.qa[v] = qa;
           }
         }
-        top = az_scan_nn(ix, s, w1);
+        top = az_scan_nn(ix, s, w1, qa.z, qa.w);
       }
       if (lane == 0) nn_finish(v, ix, s, top, w1, qa.w);
     }

@@ -89,8 +89,8 @@ __device__ void unit_prologue(CtaMem& cta, Smem& sm, const BatchView& bv, const 
   }
   __syncthreads();
   if (sm.az_ok) {
-    az_build<kAzTabS>(bv.ts + sm.ts0, sm.Ts, bv.az_s + sm.ts0, sm.azTabS, cta.u.build_tab, cta.scan_tmp, sm.nbS);
-    az_build<kAzTabC>(bv.tc + sm.tc0, sm.Tc, bv.az_c + sm.tc0, sm.azTabC, cta.u.build_tab, cta.scan_tmp, sm.nbC);
+    az_build<kAzTabS>(bv.ts + sm.ts0, sm.Ts, bv.az_s + sm.ts0, sm.azTabS, cta.u.build_tab, cta.scan_tmp, sm.nbS, sm.elevS);
+    az_build<kAzTabC>(bv.tc + sm.tc0, sm.Tc, bv.az_c + sm.tc0, sm.azTabC, cta.u.build_tab, cta.scan_tmp, sm.nbC, sm.elevC);
   }
   // queries: staged once per unit — 1-D TMA (cp.async.bulk + mbarrier) into shared memory, plain copies into the scratch
   float4* qdst = pb.qpt + (size_t)slot * bv.qtile;
