@@ -164,7 +164,7 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       const float4 s = pb.sel[v];
       const int w1 = pb.qw[v].x;
       const float4 qag = pb.qa[v];
-      const Top3 top = az_scan_nn_group<G>(ix, s, w1, qag.z, qag.w, sub, gmask);
+      const Top3 top = az_scan_nn_group<G>(ix, s, w1, qag.y, qag.w, sub, gmask);
       if (sub == 0) nn_finish(v, ix, s, top, w1, qag.w);
     }
     // P2: warps pull queries from the work list (the per-query cost is heavy-tailed; a static split leaves warps idle)
@@ -186,13 +186,13 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       if (w1 >= 0) {
         const int wp = sm.first_pass ? az_probe_window(ix, qa, w1) : -1;
         if (wp >= 0) {  // wide window (no usable previous answer): probe first, then search inside the implied window
-          const Top3 pr = az_scan_nn(ix, s, wp, qa.z, sqrtf(widen(kProbeSq)));  // (a probe needs no exactness: anything it finds is an upper bound)
+          const Top3 pr = az_scan_nn(ix, s, wp, qa.y, sqrtf(widen(kProbeSq)));  // (a probe needs no exactness: anything it finds is an upper bound)
           if (pr.p1 >= 0) {
             w1 = az_nn_window(ix, az_seed_bound(ix, s, pr.p1, nearf), qa);
             if (lane == 0) pb.qa[v] = qa;
           }
         }
-        top = az_scan_nn(ix, s, w1, qa.z, qa.w);
+        top = az_scan_nn(ix, s, w1, qa.y, qa.w);
       }
       if (lane == 0) nn_finish(v, ix, s, top, w1, qa.w);
     }

@@ -37,23 +37,29 @@ namespace lins_dev {
 struct AzIndex {
   const float4* pts;      // sorted copy (global)
   const aztab_t* bstart;  // [nrings * nb + 1], shared
-  const int (*elev)[2];   // per ring: [min, max] elevation of its targets (float_key), shared
+  const int (*elev)[2];   // per ring: [min, max] slope z / rho_xy of its targets (float_key), shared
   int nb, nrings, T;
 };
 // order-preserving float <-> int key (so that atomicMin / atomicMax on ints order floats)
 __device__ __forceinline__ int float_key(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
-__device__ __forceinline__ float elevation_of(float x, float y, float z) {
-  return atan2f(z, sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))));
+// "Elevation" of a point as the slope z / rho_xy of its ray in the (rho_xy, z) half plane (monotonic in the elevation angle;
+// no atan2f).  rho_xy == 0 gives +-inf / NaN: az_build then marks the ring's band as unbounded.
+__device__ __forceinline__ float slope_of(float x, float y, float z) {
+  return __fdiv_rn(z, sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y))));
 }
-// Lower bound (m) on the distance from a query at elevation eq and 3-D range Rq to ANY point whose elevation lies in the
-// ring's band: such a point lies on a cone about the z axis, and the query is at least Rq * sin(gap) from every cone whose
-// elevation differs from its own by gap (<= pi / 2).  0.998 and 1e-4 m absorb the f32 rounding of the angles (atan2f: a few
-// 1e-7 rad, i.e. < 1e-4 m at 100 m).  Rings with no targets report an empty band (never reached: their slices are empty).
-__device__ __forceinline__ float ring_lower_bound(const AzIndex& ix, int r, float eq, float Rq) {
+// Lower bound (m) on the distance from a query (rho_xy = rq, z = zq) to ANY point whose slope lies in the ring's band
+// [lo, hi].  The 3-D distance is at least the distance in the (rho_xy, z) half plane; there a target of slope m lies on the
+// ray t * (1, m), t >= 0, the distance from the query to a ray grows with the angle between them, and the distance to the
+// ray at the band's nearer edge m* is at least the distance to its line, |zq - m* rq| / sqrt(1 + m*^2).  0.998 and 1e-4 m
+// absorb the f32 rounding (slopes: 2 ulp -> < 2e-7 rad; the cancellation in zq - m rq: < 1e-5 m at 100 m).  An unbounded
+// band (hi - lo not finite), an overflow or a NaN anywhere makes the comparison `bound > B` false: the ring is scanned.
+__device__ __forceinline__ float ring_lower_bound(const AzIndex& ix, int r, float zq, float rq) {
   const float lo = key_float(ix.elev[r][0]), hi = key_float(ix.elev[r][1]);
-  const float gap = fminf(fmaxf(fmaxf(lo - eq, eq - hi), 0.f), 1.5707963f);
-  return Rq * (gap * (1.f - gap * gap * (1.f / 6.f))) * 0.998f - 1.0e-4f;  // sin x >= x - x^3 / 6 for x >= 0
+  const float a = __fmaf_rn(lo, rq, -zq), b = __fmaf_rn(-hi, rq, zq);  // > 0: the query lies below / above the band
+  const float m = a > b ? lo : hi;
+  const float bound = fmaxf(a, b) * rsqrtf(__fmaf_rn(m, m, 1.f)) * 0.998f - 1.0e-4f;
+  return hi - lo < 1.0e30f ? bound : -1.f;
 }
 
 __device__ __forceinline__ int az_bin(float x, float y, int nb) {
@@ -78,9 +84,9 @@ __device__ void az_build(const float4* __restrict__ src, int T, float4* dst, azt
   for (int j = threadIdx.x; j < T; j += kThreads) {
     const float4 t = __ldg(&src[j]);
     atomicAdd(&cnt[(int)t.w * nb + az_bin(t.x, t.y, nb)], 1);
-    const float e = elevation_of(t.x, t.y, t.z);
-    if (e == e) { const int k = float_key(e); atomicMin(&elev[(int)t.w][0], k); atomicMax(&elev[(int)t.w][1], k); }
-    else { atomicMin(&elev[(int)t.w][0], float_key(-3.0e38f)); atomicMax(&elev[(int)t.w][1], float_key(3.0e38f)); }  // (NaN target: never skip its ring)
+    const float e = slope_of(t.x, t.y, t.z);
+    if (fabsf(e) < 1.0e30f) { const int k = float_key(e); atomicMin(&elev[(int)t.w][0], k); atomicMax(&elev[(int)t.w][1], k); }
+    else { atomicMin(&elev[(int)t.w][0], float_key(-3.0e38f)); atomicMax(&elev[(int)t.w][1], float_key(3.0e38f)); }  // (on the z axis / NaN: never skip its ring)
   }
   __syncthreads();
   constexpr int PER = TAB / kThreads;
@@ -159,7 +165,6 @@ __device__ __forceinline__ float rejected_slack(unsigned best_bits, float Bout, 
 __device__ __forceinline__ void az_polar(const float4 s, float4& qa) {
   qa.x = atan2f(s.y, s.x);
   qa.y = sqrtf(__fadd_rn(__fmul_rn(s.x, s.x), __fmul_rn(s.y, s.y)));
-  qa.z = atan2f(s.z, qa.y);  // elevation (the same expression as elevation_of)
 }
 // window of the closest-point search given an upper bound U1 on its answer (the gate, or the distance to any real
 // target); qa.w <- distance bound of everything outside the window
@@ -296,9 +301,8 @@ __device__ __forceinline__ void az_scan_nn_slice(const AzIndex& ix, const float4
 // whose elevation band is farther than that from the query cannot hold the minimum or tie with it, like a bin outside the
 // azimuth window.
 template <int LPR>
-__device__ __forceinline__ Top3 az_scan_nn_t(const AzIndex& ix, const float4 s, int win, float eq, float Bout, long long* tm = nullptr) {
+__device__ __forceinline__ Top3 az_scan_nn_t(const AzIndex& ix, const float4 s, int win, float rq, float Bout, long long* tm = nullptr) {
   const int lane = threadIdx.x & 31;
-  const float Rq = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(s.x, s.x), __fmul_rn(s.y, s.y)), __fmul_rn(s.z, s.z)));
   const int blo = win >> 16, nbins = win & 0xffff;
   constexpr int RPP = 32 / LPR;
   const int sub = lane % LPR;
@@ -308,7 +312,7 @@ __device__ __forceinline__ Top3 az_scan_nn_t(const AzIndex& ix, const float4 s, 
   int dbg_cand = 0;
   for (int rbase = 0; rbase < ix.nrings; rbase += RPP) {
     const int r = rbase + lane / LPR;
-    if (r < ix.nrings && !(ring_lower_bound(ix, r, eq, Rq) > Bout)) {
+    if (r < ix.nrings && !(ring_lower_bound(ix, r, s.z, rq) > Bout)) {
       const int base = r * ix.nb;
       if (tm) { dbg_cand += max(0, (ix.bstart[base + e0] - ix.bstart[base + blo] - sub + LPR - 1) / LPR); if (e1 > 0) dbg_cand += max(0, (ix.bstart[base + e1] - ix.bstart[base] - sub + LPR - 1) / LPR); }
       az_scan_nn_slice<LPR>(ix, s, ix.bstart[base + blo] + sub, ix.bstart[base + e0], top);
@@ -322,10 +326,10 @@ __device__ __forceinline__ Top3 az_scan_nn_t(const AzIndex& ix, const float4 s, 
   return top;
 }
 // -> the two nearest (key, slot) pairs and the third distance, over every ring inside the window
-__device__ __forceinline__ Top3 az_scan_nn(const AzIndex& ix, const float4 s, int win, float eq, float Bout, long long* tm = nullptr) {
-  if (ix.nrings <= 8) return az_scan_nn_t<4>(ix, s, win, eq, Bout, tm);
-  if (ix.nrings <= 16) return az_scan_nn_t<2>(ix, s, win, eq, Bout, tm);
-  return az_scan_nn_t<1>(ix, s, win, eq, Bout, tm);
+__device__ __forceinline__ Top3 az_scan_nn(const AzIndex& ix, const float4 s, int win, float rq, float Bout, long long* tm = nullptr) {
+  if (ix.nrings <= 8) return az_scan_nn_t<4>(ix, s, win, rq, Bout, tm);
+  if (ix.nrings <= 16) return az_scan_nn_t<2>(ix, s, win, rq, Bout, tm);
+  return az_scan_nn_t<1>(ix, s, win, rq, Bout, tm);
 }
 
 // A GROUP of G lanes per query (G = 4: eight queries per warp): the same scans for small windows.  A warp per query
@@ -358,14 +362,13 @@ __device__ __forceinline__ void az_scan_slice_lane(const AzIndex& ix, const floa
   }
 }
 template <int G>
-__device__ __forceinline__ Top3 az_scan_nn_group(const AzIndex& ix, const float4 s, int win, float eq, float Bout, int sub, unsigned gmask) {
+__device__ __forceinline__ Top3 az_scan_nn_group(const AzIndex& ix, const float4 s, int win, float rq, float Bout, int sub, unsigned gmask) {
   const int blo = win >> 16, nbins = win & 0xffff;
   const int e0 = min(blo + nbins, ix.nb), e1 = blo + nbins - ix.nb;
-  const float Rq = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(s.x, s.x), __fmul_rn(s.y, s.y)), __fmul_rn(s.z, s.z)));
   Top3 top;
   top.init();
   for (int r = sub; r < ix.nrings; r += G) {  // rings dealt round-robin to the lanes of the group
-    if (ring_lower_bound(ix, r, eq, Rq) > Bout) continue;  // (elevation band out of reach, see az_scan_nn_t)
+    if (ring_lower_bound(ix, r, s.z, rq) > Bout) continue;  // (elevation band out of reach, see az_scan_nn_t)
     const int base = r * ix.nb;
     az_scan_slice_lane(ix, s, ix.bstart[base + blo], ix.bstart[base + e0], 1, top);
     if (e1 > 0) az_scan_slice_lane(ix, s, ix.bstart[base], ix.bstart[base + e1], 1, top);

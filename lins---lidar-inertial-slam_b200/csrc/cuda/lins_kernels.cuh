@@ -134,7 +134,7 @@ struct alignas(16) Smem {
   int nbS, nbC, nringsS, nringsC;
   aztab_t azTabS[kAzTabS + 2];  // (ring, azimuth bin) -> first slot of the sorted surf copy
   aztab_t azTabC[kAzTabC + 2];
-  // per ring: [min, max] of the elevation angle atan2(z, rho) of its targets, as order-preserving int keys (see
+  // per ring: [min, max] of the slope z / rho_xy (the tangent of the elevation angle) of its targets, as order-preserving int keys (see
   // lins_assoc_az.cuh: a ring whose elevation band is farther from the query's elevation than the search radius allows
   // is skipped by the closest-point scans)
   int elevS[kMaxRing][2], elevC[kMaxRing][2];
