@@ -434,6 +434,10 @@ __device__ __forceinline__ void az_prepare_walk(const AzIndex& ix, const float4 
 // ---- phase P4 (one WARP per query): the ring walks inside their windows -------------------------------------------
 // SURF: Ind2 over ring cr (window w2), Ind3 over rings cr-2, cr-1, cr+1, cr+2 (window w3).  Corner: Ind2 over rings
 // cr-2, cr-1, cr+1, cr+2 (window w2).  Forward candidates (original index j > c) count only while j < fwdBound.
+#ifndef LINS_WALK_IN_FLIGHT
+#define LINS_WALK_IN_FLIGHT 4
+#endif
+constexpr int kWalkInFlight = LINS_WALK_IN_FLIGHT;
 struct WalkOut {  // per class: original index (-1 = none within the gate), slot, certificate bound, runner-up slot
   int i2, i3, pos2, pos3, run2, run3;
   float bound2, bound3;
@@ -449,22 +453,28 @@ __device__ __forceinline__ WalkOut az_scan_walk(const AzIndex& ix, const float4 
   // a lane serves one ring, hence one class: it keeps a single Top3
   Top3 top;
   top.init();
-  const int r = cr - 2 + lane / 6, sub = lane % 6;  // 5 rings x 6 lanes
-  const bool cls2 = SURF ? (r == cr) : true;
-  if (lane < 30 && r >= 0 && r < ix.nrings && (SURF || r != cr)) {
+  // lanes <-> rings.  SURF: the four adjacent rings (window w3, some 40 candidates each) get 7 lanes each, the closest
+  // point's own ring (window w2, a handful) the last 4; corner: 8 lanes for each of the four adjacent rings.
+  constexpr int LPR = SURF ? 7 : 8;
+  const int q = lane / LPR;
+  const bool own = SURF && q >= 4;
+  const int r = own ? cr : cr + (q < 2 ? q - 2 : q - 1);
+  const int sub = own ? lane - 4 * LPR : lane - q * LPR, step = own ? 4 : LPR;
+  const bool cls2 = SURF ? own : true;
+  if (r >= 0 && r < ix.nrings) {
     const int win = cls2 ? w2 : w3;
     const int blo = win >> 16, nbins = win & 0xffff, base = r * ix.nb;
     for (int seg = 0; seg < 2; ++seg) {
       int p, pe;
       if (seg == 0) { p = ix.bstart[base + blo]; pe = ix.bstart[base + min(blo + nbins, ix.nb)]; }
       else { const int e1 = blo + nbins - ix.nb; if (e1 <= 0) break; p = ix.bstart[base]; pe = ix.bstart[base + e1]; }
-      for (p += sub; p < pe; p += 12) {  // two candidates in flight per lane
-        float4 tt[2];
+      for (p += sub; p < pe; p += kWalkInFlight * step) {  // kWalkInFlight candidates in flight per lane
+        float4 tt[kWalkInFlight];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) tt[u] = ld_slot(ix, p + 6 * u < pe ? p + 6 * u : p);
+        for (int u = 0; u < kWalkInFlight; ++u) tt[u] = ld_slot(ix, p + step * u < pe ? p + step * u : p);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int pu = p + 6 * u;
+        for (int u = 0; u < kWalkInFlight; ++u) {
+          const int pu = p + step * u;
           const float4 t = tt[u];
           const unsigned d = __float_as_uint(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z));
           const int j = slot_index(t.w);
@@ -478,7 +488,7 @@ __device__ __forceinline__ WalkOut az_scan_walk(const AzIndex& ix, const float4 
   }
   const float gate = sqrtf(nearf);
   const unsigned nearbits = __float_as_uint(nearf);
-  const bool mine2 = lane < 30 && cls2;  // (lanes outside the 5 x 6 layout hold the neutral entry)
+  const bool mine2 = cls2;
   Top3 neutral;
   neutral.init();
   WalkOut o;

@@ -10,7 +10,9 @@ defs = importlib.import_module("lins---lidar-inertial-slam_b200.ctypes_defs")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 config = sys.argv[3] if len(sys.argv) > 3 else "config3"
-b = synth.generate(config, n=n, seed0=1000)
+b = synth.generate(config, n=n, seed0=int(os.environ.get("QA_SEED", "1000")))
+if os.environ.get("QA_TILE"):
+    b = b.tile(int(os.environ["QA_TILE"]))
 g = capi.LinsGpu(defs.LinsParams.shipped())
 g.batch_upload(b)
 for _ in range(3):
