@@ -97,17 +97,21 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
     if (seeded) {  // certificates (lins_assoc_az.cuh: cert_accepted / cert_rejected): the stored answers still hold
       const float4 r1 = pb.qref[v], r2 = pb.qref2[v], ex = pb.qext[v];
       const unsigned nearbits = __float_as_uint(nearf);
+      const int w1s = pb.pos[3 * v], w2s = pb.pos[3 * v + 1], w3s = pb.pos[3 * v + 2];
+      const int r1s = __float_as_int(ex.y), r2s = __float_as_int(ex.z), r3s = __float_as_int(ex.w);
+      // every front-runner of the query in one batch of independent (predicated) loads
+      auto entry = [&](int slot) -> float4 { return slot >= 0 ? ixq.pts[slot] : make_float4(0.f, 0.f, 0.f, 0.f); };
+      const float4 tw1 = entry(w1s), tr1 = entry(r1s), tw2 = entry(w2s), tr2 = entry(r2s);
+      const float4 tw3 = entry(surf ? w3s : -1), tr3 = entry(surf ? r3s : -1);
       const float moved1 = sqrtf(sqdist_f32(s.x, s.y, s.z, r1.x, r1.y, r1.z));
-      const int w1s = pb.pos[3 * v];
-      const bool ok1 = w1s >= 0 ? cert_accepted<false>(ixq, s, w1s, __float_as_int(ex.y), r1.w, moved1, nearbits, 0) : cert_rejected(r1.w, moved1);
+      const bool ok1 = w1s >= 0 ? cert_accepted<false>(tw1, tr1, s, r1s, r1.w, moved1, nearbits, 0) : cert_rejected(r1.w, moved1);
       bool ok2 = false;
       const int ccr0 = pb.qccr[v];
       if (ok1 && ccr0 >= 0) {  // (the walks' candidate sets are defined by the closest point: only meaningful while it stands)
         const int c0 = ccr0 & 0x00ffffff;
         const float moved2 = sqrtf(sqdist_f32(s.x, s.y, s.z, r2.x, r2.y, r2.z));
-        const int w2s = pb.pos[3 * v + 1], w3s = pb.pos[3 * v + 2];
-        ok2 = w2s >= 0 ? cert_accepted<true>(ixq, s, w2s, __float_as_int(ex.z), r2.w, moved2, nearbits, c0) : cert_rejected(r2.w, moved2);
-        if (ok2 && surf) ok2 = w3s >= 0 ? cert_accepted<true>(ixq, s, w3s, __float_as_int(ex.w), ex.x, moved2, nearbits, c0) : cert_rejected(ex.x, moved2);
+        ok2 = w2s >= 0 ? cert_accepted<true>(tw2, tr2, s, r2s, r2.w, moved2, nearbits, c0) : cert_rejected(r2.w, moved2);
+        if (ok2 && surf) ok2 = w3s >= 0 ? cert_accepted<true>(tw3, tr3, s, r3s, ex.x, moved2, nearbits, c0) : cert_rejected(ex.x, moved2);
       }
       if (ok1 && (ok2 || ccr0 < 0)) { pb.qw[v] = make_int4(-2, 0, 0, 0); continue; }
       if (ok1) { az_polar(s, qa); pb.qa[v] = qa; pb.qw[v] = make_int4(-3, 0, 0, 0); continue; }

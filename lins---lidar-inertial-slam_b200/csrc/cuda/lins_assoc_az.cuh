@@ -380,43 +380,57 @@ __device__ __forceinline__ Top3 az_scan_nn_group(const AzIndex& ix, const float4
 
 // ---- phase P3 (one THREAD per query): bound + window the walks of a query whose closest point is (c, cr) -------
 // w2 / w3 = windows of the Ind2 / Ind3 searches, B2 / B3 = distance bound of everything outside them
-// bound from a candidate slot while it is an admissible candidate of THIS search (CLS2: the Ind2 search)
+// bound from a candidate target while it is an admissible candidate of THIS search (CLS2: the Ind2 search)
 template <bool SURF, bool CLS2>
-__device__ __forceinline__ float walk_seed_bound(const AzIndex& ix, const float4 s, int seed, int c, int cr, int fwdBound, float U) {
-  if (seed >= 0 && seed < ix.T) {
-    const float4 t = ix.pts[seed];
-    const int j = slot_index(t.w), r = slot_ring(t.w);
-    const bool ring_ok = (SURF && CLS2) ? (r == cr) : (r != cr && r >= cr - 2 && r <= cr + 2);
-    if (ring_ok && j != c && (j < c || j < fwdBound)) { const float d = sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z); if (d < U) U = d; }
-  }
-  return U;
+__device__ __forceinline__ float seed_bound(const float4 t, bool valid, const float4 s, int c, int cr, int fwdBound, float U) {
+  const int j = slot_index(t.w), r = slot_ring(t.w);
+  const bool ring_ok = (SURF && CLS2) ? (r == cr) : (r != cr && r >= cr - 2 && r <= cr + 2);
+  const float d = sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z);
+  return (valid && ring_ok && j != c && (j < c || j < fwdBound) && d < U) ? d : U;
 }
 // Uinit = NEAREST_FEATURE_SEARCH_SQ_DIST: nothing beyond the gate is accepted
 template <bool SURF>
 __device__ __forceinline__ void az_prepare_walk(const AzIndex& ix, const float4 s, const float4 qa, int p1, int c, int cr, int seed2,
                                                 int seed3, int fwdBound, float Uinit, int& w2, int& w3, float& B2, float& B3) {
-  // bounds from the previous answers ...
-  float U2 = walk_seed_bound<SURF, true>(ix, s, seed2, c, cr, fwdBound, Uinit);
-  float U3 = SURF ? walk_seed_bound<SURF, false>(ix, s, seed3, c, cr, fwdBound, Uinit) : Uinit;
-  // ... and from the index neighbourhood of the closest point / of the query's azimuth on the adjacent rings.  Each is
-  // used only while it is an admissible candidate of the search it bounds (walk_seed_bound), so the windows shrink
-  // (a unit's first pass has no previous answers: gate-wide windows otherwise) and exactness is untouched.
-  if (SURF) {
+  // Bounds from the previous answers and from the index neighbourhood of the closest point / of the query's azimuth on
+  // the adjacent rings.  Each is used only while it is an admissible candidate of the search it bounds (seed_bound), so
+  // the windows shrink (a unit's first pass has no previous answers: gate-wide windows otherwise) and exactness is
+  // untouched.  The look-ups are independent: all loads of a batch are issued before the first is used (one L2 round
+  // trip per batch instead of one per seed).
+  auto fetch = [&](int seed, bool& valid) -> float4 {
+    valid = seed >= 0 && seed < ix.T;
+    return valid ? ix.pts[seed] : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float U2 = Uinit, U3 = Uinit;
+  {
+    constexpr int NA = SURF ? 6 : 1;
+    const int seeds[6] = {seed2, seed3, p1 - 2, p1 - 1, p1 + 1, p1 + 2};
+    float4 t[NA];
+    bool ok[NA];
 #pragma unroll
-    for (int d = -2; d <= 2; ++d)
-      if (d != 0) U2 = walk_seed_bound<true, true>(ix, s, p1 + d, c, cr, fwdBound, U2);
+    for (int k = 0; k < NA; ++k) t[k] = fetch(seeds[k], ok[k]);
+    U2 = seed_bound<SURF, true>(t[0], ok[0], s, c, cr, fwdBound, U2);
+    if (SURF) {
+      U3 = seed_bound<SURF, false>(t[1 % NA], ok[1 % NA], s, c, cr, fwdBound, U3);
+#pragma unroll
+      for (int k = 2; k < NA; ++k) U2 = seed_bound<true, true>(t[k], ok[k], s, c, cr, fwdBound, U2);
+    }
   }
   {
     const int bq = az_bin_of_angle(qa.x, ix.nb);
     float& U = SURF ? U3 : U2;
+    float4 t[8];
+    bool ok[8];
 #pragma unroll
-    for (int dr = -2; dr <= 2; ++dr) {
-      const int r = cr + dr;
-      if (dr == 0 || r < 0 || r >= ix.nrings) continue;
-      const int slot = ix.bstart[r * ix.nb + bq];
-      U = walk_seed_bound<SURF, !SURF>(ix, s, slot, c, cr, fwdBound, U);
-      U = walk_seed_bound<SURF, !SURF>(ix, s, slot - 1, c, cr, fwdBound, U);
+    for (int k = 0; k < 4; ++k) {
+      const int r = cr + (k < 2 ? k - 2 : k - 1);
+      const bool rok = r >= 0 && r < ix.nrings;
+      const int slot = rok ? (int)ix.bstart[r * ix.nb + bq] : -1;
+      t[2 * k] = fetch(slot, ok[2 * k]);
+      t[2 * k + 1] = fetch(rok ? slot - 1 : -1, ok[2 * k + 1]);
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) U = seed_bound<SURF, !SURF>(t[k], ok[k], s, c, cr, fwdBound, U);
   }
   int blo, nbins;
   const float Uw2 = widen(U2);
@@ -570,20 +584,21 @@ __device__ __forceinline__ WalkOut az_scan_walk_group(const AzIndex& ix, const f
 //     exceeded at the search position and `moved` the displacement since (distances change by at most that much);
 //     2e-4 m absorbs the f32 rounding of the distances involved.
 // WALK: keys carry the visiting order relative to the closest point c instead of the original index.
+// tw / tr = the winner's / runner-up's entry of the sorted copy, loaded by the caller (all of a query's front-runners are
+// fetched in one batch: one L2 round trip instead of up to six dependent ones); r < 0 = no runner-up.
 template <bool WALK>
-__device__ __forceinline__ bool cert_accepted(const AzIndex& ix, const float4 s, int w, int r, float bound, float moved, unsigned nearbits,
+__device__ __forceinline__ bool cert_accepted(const float4 tw, const float4 tr, const float4 s, int r, float bound, float moved, unsigned nearbits,
                                               int c) {
-  auto key_of = [&](int slot) -> unsigned long long {
-    const float4 t = ix.pts[slot];
+  auto key_of = [&](const float4 t) -> unsigned long long {
     const unsigned d = __float_as_uint(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z));
     const int j = slot_index(t.w);
     const unsigned lo = WALK ? (j > c ? order_fwd(j) : order_bwd(j)) : (unsigned)j;
     return ((unsigned long long)d << 32) | lo;
   };
-  const unsigned long long kw = key_of(w);
+  const unsigned long long kw = key_of(tw);
   const unsigned dw = (unsigned)(kw >> 32);
   if (!(dw < nearbits)) return false;
-  if (r >= 0 && !(kw < key_of(r))) return false;
+  if (r >= 0 && !(kw < key_of(tr))) return false;
   return sqrtf(__uint_as_float(dw)) + moved + 2.0e-4f < bound;
 }
 // a search that found nothing within the gate: stays that way while the query moved less than half the slack
