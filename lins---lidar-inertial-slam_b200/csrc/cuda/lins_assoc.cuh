@@ -99,15 +99,21 @@ __device__ void association_pass(CtaMem& cta, Smem* slots, const BatchView& bv, 
       const unsigned nearbits = __float_as_uint(nearf);
       const int w1s = pb.pos[3 * v], w2s = pb.pos[3 * v + 1], w3s = pb.pos[3 * v + 2];
       const int r1s = __float_as_int(ex.y), r2s = __float_as_int(ex.z), r3s = __float_as_int(ex.w);
-      // every front-runner of the query in one batch of independent (predicated) loads
-      auto entry = [&](int slot) -> float4 { return slot >= 0 ? ixq.pts[slot] : make_float4(0.f, 0.f, 0.f, 0.f); };
-      const float4 tw1 = entry(w1s), tr1 = entry(r1s), tw2 = entry(w2s), tr2 = entry(r2s);
-      const float4 tw3 = entry(surf ? w3s : -1), tr3 = entry(surf ? r3s : -1);
+      // every front-runner of the query in one batch of independent (predicated) loads; a slot is read only where the
+      // sequential evaluation below could use it (the runner-up fields of a rejected search and the walk fields of a query
+      // without a closest point are not maintained)
+      const int ccr0 = pb.qccr[v];
+      const bool walks = ccr0 >= 0;
+      auto entry = [&](int slot, bool use) -> float4 {
+        return use && slot >= 0 && slot < ixq.T ? ixq.pts[slot] : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      const float4 tw1 = entry(w1s, true), tr1 = entry(r1s, w1s >= 0);
+      const float4 tw2 = entry(w2s, walks), tr2 = entry(r2s, walks && w2s >= 0);
+      const float4 tw3 = entry(w3s, walks && surf), tr3 = entry(r3s, walks && surf && w3s >= 0);
       const float moved1 = sqrtf(sqdist_f32(s.x, s.y, s.z, r1.x, r1.y, r1.z));
       const bool ok1 = w1s >= 0 ? cert_accepted<false>(tw1, tr1, s, r1s, r1.w, moved1, nearbits, 0) : cert_rejected(r1.w, moved1);
       bool ok2 = false;
-      const int ccr0 = pb.qccr[v];
-      if (ok1 && ccr0 >= 0) {  // (the walks' candidate sets are defined by the closest point: only meaningful while it stands)
+      if (ok1 && walks) {  // (the walks' candidate sets are defined by the closest point: only meaningful while it stands)
         const int c0 = ccr0 & 0x00ffffff;
         const float moved2 = sqrtf(sqdist_f32(s.x, s.y, s.z, r2.x, r2.y, r2.z));
         ok2 = w2s >= 0 ? cert_accepted<true>(tw2, tr2, s, r2s, r2.w, moved2, nearbits, c0) : cert_rejected(r2.w, moved2);
