@@ -452,6 +452,10 @@ __device__ __forceinline__ void az_prepare_walk(const AzIndex& ix, const float4 
 #define LINS_WALK_IN_FLIGHT 4
 #endif
 constexpr int kWalkInFlight = LINS_WALK_IN_FLIGHT;
+#ifndef LINS_GROUP_WALK_IN_FLIGHT
+#define LINS_GROUP_WALK_IN_FLIGHT 4
+#endif
+constexpr int kGroupWalkInFlight = LINS_GROUP_WALK_IN_FLIGHT;
 struct WalkOut {  // per class: original index (-1 = none within the gate), slot, certificate bound, runner-up slot
   int i2, i3, pos2, pos3, run2, run3;
   float bound2, bound3;
@@ -536,11 +540,12 @@ __device__ __forceinline__ WalkOut az_scan_walk_group(const AzIndex& ix, const f
       int p, pe;
       if (seg == 0) { p = ix.bstart[base + blo]; pe = ix.bstart[base + min(blo + nbins, ix.nb)]; }
       else { const int e1 = blo + nbins - ix.nb; if (e1 <= 0) break; p = ix.bstart[base]; pe = ix.bstart[base + e1]; }
-      for (p += start; p < pe; p += 2 * step) {
-        float4 tt[2];
-        tt[0] = ld_slot(ix, p); tt[1] = ld_slot(ix, p + step < pe ? p + step : p);
+      for (p += start; p < pe; p += kGroupWalkInFlight * step) {
+        float4 tt[kGroupWalkInFlight];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < kGroupWalkInFlight; ++u) tt[u] = ld_slot(ix, p + u * step < pe ? p + u * step : p);
+#pragma unroll
+        for (int u = 0; u < kGroupWalkInFlight; ++u) {
           const int pu = p + u * step;
           const float4 t = tt[u];
           const unsigned d = __float_as_uint(sqdist_f32(t.x, t.y, t.z, s.x, s.y, s.z));
