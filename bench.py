@@ -90,6 +90,33 @@ def bind_to_gpu_numa_node(local):
         return f"not bound ({type(e).__name__})"
 
 
+def host_memory_policy(interleave):
+    """set_mempolicy(MPOL_INTERLEAVE over the online NUMA nodes) / (MPOL_DEFAULT) for what this process allocates from here
+    on: what `numactl --interleave=all` does for a replay job's host clouds and the library's pinned staging.  The pack
+    threads and the copy engines read them from both sockets; with first-touch placement the end-to-end rate depended on
+    which socket the clouds happened to land on (measured on the 2-socket B200 host, 3 contexts x 21 pack threads:
+    5.6-6.2 M it/s first-touch, 7.7-7.9 M interleaved).  The CPU arms keep the default policy (thread-private matrices)."""
+    try:
+        import ctypes
+        nodes = []
+        for part in open("/sys/devices/system/node/online").read().strip().split(","):
+            a, _, b = part.partition("-")
+            nodes += list(range(int(a), int(b or a) + 1))
+        if len(nodes) < 2:
+            return "one NUMA node"
+        libc = ctypes.CDLL(None, use_errno=True)
+        if interleave:
+            mask = ctypes.c_ulong(sum(1 << n for n in nodes))
+            rc = libc.syscall(ctypes.c_long(238), ctypes.c_long(3), ctypes.byref(mask), ctypes.c_ulong(max(nodes) + 2))  # x86-64 set_mempolicy, MPOL_INTERLEAVE
+        else:
+            rc = libc.syscall(ctypes.c_long(238), ctypes.c_long(0), None, ctypes.c_ulong(0))  # MPOL_DEFAULT
+        if rc != 0:
+            return f"set_mempolicy refused (errno {ctypes.get_errno()})"
+        return f"host buffers interleaved over NUMA nodes {nodes}" if interleave else "default policy"
+    except (OSError, ValueError, AttributeError) as e:
+        return f"not interleaved ({type(e).__name__})"
+
+
 def thread_sweep(cores):
     return sorted({max(1, cores // 4), max(1, cores // 2), cores})
 
@@ -258,6 +285,8 @@ def main():
     # (opt-in: measured on the 2-socket B200 host it LOWERED the 2-GPU e2e — 12.2 -> 9.8 M it/s with host pack, 7.7 -> 6.1 M
     # with raw DMA — because it halves the CPUs the rank's pack threads and copy threads may use)
     numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("LINS_NUMA_BIND", "0") == "1" else "not bound"
+    if os.environ.get("LINS_NUMA_INTERLEAVE", "1") != "0":  # (the replay job's host buffers; the CPU legs below reset it)
+        numa += "; " + host_memory_policy(True)
     # host threads each lins_gpu_batch_upload may use for packing: the cores are shared by `world` ranks x 3 contexts
     os.environ.setdefault("LINS_PACK_THREADS", str(max(2, min(32, (os.cpu_count() or 8) // (max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))) * 6)))))
     # a non-default torch stream: its handle is non-NULL, so the library launches on it (NULL would make the
@@ -359,7 +388,8 @@ def main():
     # calls in flight (each is synchronous).  Measured on the B200 box (128 host cores): 3 contexts 3.8 M it/s,
     # 6 contexts 2.1 M, 9 contexts 2.2 M — more host threads than that only contend
     NE = int(os.environ.get("LINS_E2E_CONTEXTS", "3"))
-    e2e_steps = max(NE, min(2 * args.steps, 24))
+    # (a step is 2-4 ms: a short sample mostly times the start of the worker threads; 8 x steps keeps the spread under a few %)
+    e2e_steps = max(NE, int(os.environ.get("LINS_E2E_STEPS", 8 * args.steps)))
     e2e_streams = [torch.cuda.Stream(device=local) for _ in range(max(0, NE - NB))]  # (kept alive until the end of main)
     e2e_ctxs = (ctxs + [capi.LinsGpu(prm, device=local, stream=st.cuda_stream) for st in e2e_streams])[:NE]
     # the replay job's host clouds are page-locked once (lins_gpu_host_register): the library then DMAs the raw 32-B
@@ -434,6 +464,7 @@ def main():
     for pb in pbatches:
         capi.unpin_batch(pb)
     del pbatches
+    host_memory_policy(False)  # (the oracle legs below allocate thread-private matrices: first-touch placement)
     b0 = batches[0]
     pts = sum(int(b0.offsets[k][-1]) for k in b0.FIELDS)
     # caller-pinned clouds are split at run time between the pack threads (16 B / point over PCIe) and the copy engine (raw
