@@ -285,7 +285,10 @@ def main():
     # (opt-in: measured on the 2-socket B200 host it LOWERED the 2-GPU e2e — 12.2 -> 9.8 M it/s with host pack, 7.7 -> 6.1 M
     # with raw DMA — because it halves the CPUs the rank's pack threads and copy threads may use)
     numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("LINS_NUMA_BIND", "0") == "1" else "not bound"
-    if os.environ.get("LINS_NUMA_INTERLEAVE", "1") != "0":  # (the replay job's host buffers; the CPU legs below reset it)
+    # The replay job's host buffers are interleaved over the NUMA nodes (pack threads and copy engines read them from both
+    # sockets).  Measured: 1 GPU 5.6-6.2 M it/s first-touch -> 7.7-7.9 M interleaved (five runs of five); 2 GPUs on one box,
+    # one run each: 7.1 M first-touch, 7.5 M interleaved.  LINS_NUMA_INTERLEAVE=0 turns it off.
+    if os.environ.get("LINS_NUMA_INTERLEAVE", "1") != "0":  # (the CPU legs below reset the policy)
         numa += "; " + host_memory_policy(True)
     # host threads each lins_gpu_batch_upload may use for packing: the cores are shared by `world` ranks x 3 contexts
     os.environ.setdefault("LINS_PACK_THREADS", str(max(2, min(32, (os.cpu_count() or 8) // (max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))) * 6)))))
