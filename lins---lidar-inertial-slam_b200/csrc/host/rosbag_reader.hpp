@@ -13,8 +13,9 @@
 // connection header with type / md5sum / message_definition), 0x02 message data (conn, time; data = serialised message),
 // 0x04 index data, 0x06 chunk info.  All integers little endian; time = u32 sec + u32 nsec.
 // This reader walks the records in file order (the index sections are skipped, so truncated / unindexed bags still
-// read); chunks with compression "none" are parsed in place, "bz2" / "lz4" chunks are reported as LINS_BAG_E_COMPRESSED
-// (tools/bag_tool.py decompresses a bag with Python's bz2 module).
+// read); chunks with compression "none" are parsed in place, "lz4" chunks (one LZ4 frame per chunk, as ros_comm's roslz4
+// writes them) are inflated by the decoder below, "bz2" chunks are reported as LINS_BAG_E_COMPRESSED
+// (`tools/bag_tool.py decompress` rewrites such a bag with Python's bz2 module).
 #ifndef LINS_HOST_ROSBAG_READER_HPP_
 #define LINS_HOST_ROSBAG_READER_HPP_
 
@@ -105,6 +106,72 @@ inline bool field_as(const Fields& f, const char* name, T& v) {
   return true;
 }
 
+// ---- LZ4 (public formats) ----------------------------------------------------------------------------------------------
+// Block: sequences of <token: literal length << 4 | match length - 4> [length bytes while 255] <literals> <u16 offset>
+// [length bytes]; a match copies byte by byte from `offset` back in the output (it may overlap itself); the last sequence
+// has literals only.  Appends to `out`, never beyond `limit` bytes; earlier output stays addressable (linked blocks).
+inline bool lz4_block_decode(const uint8_t* s, size_t n, std::vector<uint8_t>& out, size_t limit) {
+  const uint8_t* const e = s + n;
+  while (s < e) {
+    const unsigned tok = *s++;
+    size_t ll = tok >> 4;
+    if (ll == 15) {
+      unsigned b;
+      do { if (s >= e) return false; b = *s++; ll += b; } while (b == 255);
+    }
+    if ((size_t)(e - s) < ll || limit - out.size() < ll) return false;
+    out.insert(out.end(), s, s + ll);
+    s += ll;
+    if (s >= e) break;
+    if (e - s < 2) return false;
+    const size_t off = (size_t)s[0] | ((size_t)s[1] << 8);
+    s += 2;
+    if (off == 0 || off > out.size()) return false;
+    size_t ml = tok & 15u;
+    if (ml == 15) {
+      unsigned b;
+      do { if (s >= e) return false; b = *s++; ml += b; } while (b == 255);
+    }
+    ml += 4;
+    if (limit - out.size() < ml) return false;
+    const size_t from = out.size() - off;
+    out.resize(out.size() + ml);
+    uint8_t* d = out.data() + from + off;
+    const uint8_t* m = out.data() + from;
+    for (size_t i = 0; i < ml; ++i) d[i] = m[i];
+  }
+  return true;
+}
+// Frame: magic 0x184D2204, FLG (version 01, block independence, block checksum, content size, content checksum, dict id),
+// BD, [u64 content size], [u32 dict id], header checksum, blocks <u32 size; bit 31 = stored raw> [u32 block checksum],
+// end mark 0, [u32 content checksum].  Checksums are skipped, not verified (the chunk's record carries its inflated size).
+inline bool lz4_frame_decode(const uint8_t* s, size_t n, std::vector<uint8_t>& out, size_t limit) {
+  Cursor c(s, n);
+  if (c.get<uint32_t>() != 0x184D2204u) return false;
+  const uint8_t flg = c.get<uint8_t>();
+  c.get<uint8_t>();  // BD: the block maximum size (the output limit bounds the work instead)
+  if (!c.ok || (flg >> 6) != 1) return false;
+  if (flg & 0x08) c.get<uint64_t>();
+  if (flg & 0x01) c.get<uint32_t>();
+  c.get<uint8_t>();
+  for (;;) {
+    uint32_t bs = c.get<uint32_t>();
+    if (!c.ok) return false;
+    if (bs == 0) return true;
+    const bool raw = (bs >> 31) != 0;
+    bs &= 0x7fffffffu;
+    const uint8_t* b = c.bytes(bs);
+    if (!b) return false;
+    if (raw) {
+      if (limit - out.size() < bs) return false;
+      out.insert(out.end(), b, b + bs);
+    } else if (!lz4_block_decode(b, bs, out, limit)) {
+      return false;
+    }
+    if (flg & 0x10) c.get<uint32_t>();
+  }
+}
+
 // ---- reader -------------------------------------------------------------------------------------------------------------
 class Reader {
  public:
@@ -156,6 +223,16 @@ class Reader {
           break;
         case 0x05: {
           const std::string comp = f.count("compression") ? f["compression"] : "none";
+          if (comp == "lz4") {
+            uint32_t size = 0;
+            if (!field_as(f, "size", size) || size > (1u << 30)) { error = "lz4 chunk without a sane size"; return LINS_BAG_E_FORMAT; }
+            std::vector<uint8_t> inflated;  // (messages are handed to fn during the walk: the buffer only has to outlive it)
+            inflated.reserve(size);
+            if (!lz4_frame_decode(db, dl, inflated, size) || inflated.size() != size) { error = "corrupt lz4 chunk"; return LINS_BAG_E_FORMAT; }
+            const int rc = walk(inflated.data(), inflated.size(), fn, false);
+            if (rc != LINS_BAG_OK) return rc;
+            break;
+          }
           if (comp != "none") { error = "chunk compression '" + comp + "' (run tools/bag_tool.py decompress first)"; return LINS_BAG_E_COMPRESSED; }
           const int rc = walk(db, dl, fn, false);
           if (rc != LINS_BAG_OK) return rc;

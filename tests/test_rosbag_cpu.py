@@ -132,3 +132,117 @@ def test_compressed_and_damaged_bags(baglib, tmp_path):
     g.write_bytes(b"not a bag at all")
     assert _summary(baglib, str(g))[0] == -2
     assert _summary(baglib, str(tmp_path / "missing.bag"))[0] == -1
+
+
+# ---- "lz4" chunk compression (one LZ4 frame per chunk, ros_comm's roslz4) ---------------------------------------------------
+def _liblz4():
+    import ctypes.util
+    name = C.util.find_library("lz4")
+    if not name:
+        pytest.skip("no system liblz4 to pin the codec against")
+    L = C.CDLL(name)
+    L.LZ4F_compressFrameBound.restype = C.c_size_t
+    L.LZ4F_compressFrameBound.argtypes = [C.c_size_t, C.c_void_p]
+    L.LZ4F_compressFrame.restype = C.c_size_t
+    L.LZ4F_compressFrame.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.LZ4F_isError.argtypes = [C.c_size_t]
+    L.LZ4F_createDecompressionContext.argtypes = [C.POINTER(C.c_void_p), C.c_uint]
+    L.LZ4F_createDecompressionContext.restype = C.c_size_t
+    L.LZ4F_decompress.restype = C.c_size_t
+    L.LZ4F_decompress.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p, C.POINTER(C.c_size_t), C.c_void_p]
+    L.LZ4F_freeDecompressionContext.argtypes = [C.c_void_p]
+    return L
+
+
+def _payloads():
+    rng = np.random.default_rng(2)
+    conns, msgs, _ = bag_tool.fixture_contents()
+    return [b"", b"a", b"abcd" * 3, b"x" * 13, b"\x00" * 70000, b"hello world, " * 9000,
+            bytes(rng.integers(0, 256, 100000, dtype=np.uint8)),  # incompressible: stored raw
+            bytes(rng.integers(0, 4, 300000, dtype=np.uint8)),    # several 64-KiB blocks, long literal / match lengths
+            b"".join(m for _, _, m in msgs)]                      # real message bytes
+
+
+def test_lz4_codec_round_trips_and_matches_the_system_liblz4():
+    for data in _payloads():
+        frame = bag_tool.lz4_frame_compress(data)
+        assert bag_tool.lz4_frame_decompress(frame, len(data)) == data
+    L = _liblz4()
+    for data in _payloads():
+        # the real library's frames (linked blocks by default) through our decoder
+        cap = L.LZ4F_compressFrameBound(len(data), None)
+        dst = C.create_string_buffer(cap)
+        n = L.LZ4F_compressFrame(dst, cap, data, len(data), None)
+        assert not L.LZ4F_isError(n)
+        assert bag_tool.lz4_frame_decompress(dst.raw[:n], len(data)) == data
+        # our frames (header checksum = our XXH32) through the real library's decoder
+        frame = bag_tool.lz4_frame_compress(data)
+        ctx = C.c_void_p()
+        assert not L.LZ4F_isError(L.LZ4F_createDecompressionContext(C.byref(ctx), 100))
+        out = C.create_string_buffer(max(1, len(data)))
+        got, pos = b"", 0
+        while pos < len(frame):
+            dn, sn = C.c_size_t(len(out)), C.c_size_t(len(frame) - pos)
+            src = (C.c_char * sn.value).from_buffer_copy(frame[pos:])
+            rc = L.LZ4F_decompress(ctx, out, C.byref(dn), src, C.byref(sn), None)
+            assert not L.LZ4F_isError(rc)
+            got += out.raw[: dn.value]
+            pos += sn.value
+            if rc == 0:
+                break
+        L.LZ4F_freeDecompressionContext(ctx)
+        assert got == data and pos == len(frame)
+
+
+def test_cpp_reader_inflates_lz4_chunks(baglib, tmp_path):
+    conns, msgs, _ = bag_tool.fixture_contents()
+    z = str(tmp_path / "lz4.bag")
+    bag_tool.write_bag(z, conns, msgs, compression="lz4", chunk_bytes=1 << 14)  # several chunks
+    assert os.path.getsize(z) < os.path.getsize(FIX)
+    ref_rc, ref_text = _summary(baglib, FIX)
+    rc, text = _summary(baglib, z)
+    assert rc == 0 and ref_rc == 0 and text == ref_text
+    # every IMU sample and every cloud byte identical to the uncompressed fixture
+    for path_a, path_b in [(FIX, z)]:
+        outs = []
+        for p in (path_a, path_b):
+            imu = np.zeros((4096, 11))
+            n = C.c_int(0)
+            assert baglib.lins_bag_read_imu(p.encode(), b"/imu/data", imu.ctypes.data, 4096, C.byref(n)) == 0
+            pts = np.zeros((1 << 16, 8), dtype=np.float32)
+            m, st = C.c_int(0), C.c_double(0)
+            assert baglib.lins_bag_read_cloud(p.encode(), b"/velodyne_points", 0, pts.ctypes.data, 1 << 16, C.byref(m), C.byref(st)) == 0
+            outs.append((imu[: n.value].copy(), pts[: m.value].copy(), st.value))
+        assert outs[0][0].shape == outs[1][0].shape and np.array_equal(outs[0][0], outs[1][0])
+        assert outs[0][1].shape[0] > 0 and np.array_equal(outs[0][1], outs[1][1]) and outs[0][2] == outs[1][2]
+    # chunks compressed by the system liblz4 (linked blocks, its own match finder) read the same
+    import ctypes.util
+    if C.util.find_library("lz4"):
+        L = _liblz4()
+
+        def real(data):
+            cap = L.LZ4F_compressFrameBound(len(data), None)
+            dst = C.create_string_buffer(cap)
+            n = L.LZ4F_compressFrame(dst, cap, data, len(data), None)
+            assert not L.LZ4F_isError(n)
+            return dst.raw[:n]
+
+        zr = str(tmp_path / "lz4_real.bag")
+        bag_tool.write_bag(zr, conns, msgs, compression="lz4", chunk_bytes=1 << 17, lz4_compress=real)
+        rc, text = _summary(baglib, zr)
+        assert rc == 0 and text == ref_text
+        pts = np.zeros((1 << 16, 8), dtype=np.float32)
+        m, st = C.c_int(0), C.c_double(0)
+        assert baglib.lins_bag_read_cloud(zr.encode(), b"/velodyne_points", 0, pts.ctypes.data, 1 << 16, C.byref(m), C.byref(st)) == 0
+        assert np.array_equal(pts[: m.value], outs[0][1])
+    # the Python reader reads it back too, and a corrupted frame is rejected, not mis-parsed
+    c2, m2 = bag_tool.read_bag(z)
+    assert [x[2] for x in m2] == [x[2] for x in msgs]
+    raw = bytearray(open(z, "rb").read())
+    k = raw.find(b"\x04\x22\x4d\x18")
+    assert k > 0
+    bad = tmp_path / "bad.bag"
+    raw[k + 40 : k + 60] = b"\xff" * 20
+    bad.write_bytes(bytes(raw))
+    rc, text = _summary(baglib, str(bad))
+    assert rc == -2 and "lz4" in text

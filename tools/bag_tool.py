@@ -1,12 +1,12 @@
 #!/usr/bin/env python
-"""tools/bag_tool.py — a pure-Python ROS1 bag v2.0 reader / writer (struct + bz2 only; no ROS).
+"""tools/bag_tool.py — a pure-Python ROS1 bag v2.0 reader / writer (struct + bz2 + an own LZ4 codec; no ROS).
 
 Independent of csrc/host/rosbag_reader.hpp on purpose: the two implementations check each other in
 tests/test_rosbag_cpu.py (Python writes -> C++ reads, C++ writes -> Python reads).
 
   python tools/bag_tool.py info X.bag               topics, types, counts, time span
-  python tools/bag_tool.py decompress IN.bag OUT.bag   rewrite with uncompressed chunks (bz2 chunks are inflated; the C++
-                                                       reader handles compression "none" only)
+  python tools/bag_tool.py decompress IN.bag OUT.bag   rewrite with uncompressed chunks (bz2 / lz4 chunks are inflated; the C++
+                                                       reader handles "none" and "lz4" itself)
   python tools/bag_tool.py make-fixture OUT.bag     the small synthetic fixture committed as tests/golden/tiny.bag
 
 Format: wiki.ros.org/Bags/Format/2.0 (records = <u32 hlen><header fields><u32 dlen><data>; field = <u32 len>name=value).
@@ -19,6 +19,155 @@ import numpy as np
 
 MAGIC = b"#ROSBAG V2.0\n"
 OP_MSG, OP_BAGHDR, OP_INDEX, OP_CHUNK, OP_CHUNKINFO, OP_CONN = 2, 3, 4, 5, 6, 7
+
+
+# ---- LZ4 (the "lz4" chunk compression of rosbag = one LZ4 frame per chunk, written by ros_comm's roslz4) --------------------
+# Public formats: LZ4 frame (magic 0x184D2204, FLG, BD, optional content size / dictionary id, header checksum, blocks
+# <u32 size, bit 31 = stored raw>, end mark 0, optional content checksum) and LZ4 block (sequences: token = literal length
+# << 4 | match length - 4, 15 = continued in following bytes; literals; u16 offset; match copied byte by byte, may overlap).
+LZ4_MAGIC = 0x184D2204
+
+
+def lz4_block_decompress(src, out):
+    """appends the decoded block to bytearray `out` (earlier output stays addressable: linked blocks work too)"""
+    i, n = 0, len(src)
+    while i < n:
+        tok = src[i]; i += 1
+        ll = tok >> 4
+        if ll == 15:
+            while True:
+                if i >= n:
+                    raise ValueError("lz4: truncated literal length")
+                b = src[i]; i += 1; ll += b
+                if b != 255:
+                    break
+        if i + ll > n:
+            raise ValueError("lz4: literals run past the block")
+        out += src[i:i + ll]; i += ll
+        if i >= n:
+            break  # the last sequence of a block is literals only
+        if i + 2 > n:
+            raise ValueError("lz4: truncated offset")
+        off = src[i] | (src[i + 1] << 8); i += 2
+        if off == 0 or off > len(out):
+            raise ValueError("lz4: offset outside the output")
+        ml = tok & 15
+        if ml == 15:
+            while True:
+                if i >= n:
+                    raise ValueError("lz4: truncated match length")
+                b = src[i]; i += 1; ml += b
+                if b != 255:
+                    break
+        ml += 4
+        start = len(out) - off
+        if off >= ml:
+            out += out[start:start + ml]
+        else:  # overlapping match: the pattern of `off` bytes repeats
+            pat = bytes(out[start:])
+            out += (pat * (ml // off + 1))[:ml]
+
+
+def lz4_frame_decompress(b, expected=None):
+    if len(b) < 7 or struct.unpack_from("<I", b, 0)[0] != LZ4_MAGIC:
+        raise ValueError("lz4: not an LZ4 frame")
+    flg = b[4]
+    if flg >> 6 != 1:
+        raise ValueError("lz4: unsupported frame version")
+    i = 6 + (8 if flg & 0x08 else 0) + (4 if flg & 0x01 else 0) + 1  # FLG, BD, [content size], [dict id], header checksum
+    out = bytearray()
+    while True:
+        if i + 4 > len(b):
+            raise ValueError("lz4: frame without end mark")
+        (bs,) = struct.unpack_from("<I", b, i); i += 4
+        if bs == 0:
+            break
+        raw, bs = bs >> 31, bs & 0x7FFFFFFF
+        if i + bs > len(b):
+            raise ValueError("lz4: truncated block")
+        if raw:
+            out += b[i:i + bs]
+        else:
+            lz4_block_decompress(b[i:i + bs], out)
+        i += bs + (4 if flg & 0x10 else 0)
+    if expected is not None and len(out) != expected:
+        raise ValueError(f"lz4: chunk inflates to {len(out)} bytes, record says {expected}")
+    return bytes(out)
+
+
+def _xxh32(data, seed=0):
+    """XXH32 (public algorithm) — the LZ4 frame header checksum is its second byte"""
+    P1, P2, P3, P4, P5, M = 2654435761, 2246822519, 3266489917, 668265263, 374761393, 0xFFFFFFFF
+    rotl = lambda x, r: ((x << r) | (x >> (32 - r))) & M
+    n, i = len(data), 0
+    if n >= 16:
+        v = [(seed + P1 + P2) & M, (seed + P2) & M, seed & M, (seed - P1) & M]
+        while i + 16 <= n:
+            for k in range(4):
+                v[k] = (rotl((v[k] + struct.unpack_from("<I", data, i + 4 * k)[0] * P2) & M, 13) * P1) & M
+            i += 16
+        h = (rotl(v[0], 1) + rotl(v[1], 7) + rotl(v[2], 12) + rotl(v[3], 18)) & M
+    else:
+        h = (seed + P5) & M
+    h = (h + n) & M
+    while i + 4 <= n:
+        h = (rotl((h + struct.unpack_from("<I", data, i)[0] * P3) & M, 17) * P4) & M; i += 4
+    while i < n:
+        h = (rotl((h + data[i] * P5) & M, 11) * P1) & M; i += 1
+    h ^= h >> 15; h = (h * P2) & M; h ^= h >> 13; h = (h * P3) & M; h ^= h >> 16
+    return h
+
+
+def lz4_block_compress(src):
+    """greedy single-probe hash matcher (what the writer and the tests need; ratio is not the point).  Ends the block the
+    way the format demands: the last 5 bytes are literals and no match starts within the last 12 bytes."""
+    n, out, anchor, i, table = len(src), bytearray(), 0, 0, {}
+
+    def emit(lit, ml, off):
+        ll = len(lit)
+        out.append((min(ll, 15) << 4) | (min(ml - 4, 15) if ml else 0))
+        if ll >= 15:
+            r = ll - 15
+            while r >= 255:
+                out.append(255); r -= 255
+            out.append(r)
+        out.extend(lit)
+        if ml:
+            out.extend(struct.pack("<H", off))
+            if ml - 4 >= 15:
+                r = ml - 4 - 15
+                while r >= 255:
+                    out.append(255); r -= 255
+                out.append(r)
+
+    while i + 12 < n:
+        key = src[i:i + 4]
+        j = table.get(key, -1)
+        table[key] = i
+        if j >= 0 and i - j <= 0xFFFF:
+            ml = 4
+            while i + ml < n - 5 and src[j + ml] == src[i + ml]:
+                ml += 1
+            emit(src[anchor:i], ml, i - j)
+            i += ml; anchor = i
+        else:
+            i += 1
+    emit(src[anchor:], 0, 0)
+    return bytes(out)
+
+
+def lz4_frame_compress(b, block_bytes=1 << 16):
+    """an LZ4 frame like roslz4's: version 01, independent blocks, no checksums but the header's"""
+    desc = bytes([(1 << 6) | (1 << 5), {1 << 16: 4, 1 << 18: 5, 1 << 20: 6, 1 << 22: 7}[block_bytes] << 4])
+    out = bytearray(struct.pack("<I", LZ4_MAGIC) + desc + bytes([(_xxh32(desc) >> 8) & 0xFF]))
+    for i in range(0, len(b), block_bytes):
+        raw = b[i:i + block_bytes]
+        c = lz4_block_compress(raw)
+        if len(c) < len(raw):
+            out += struct.pack("<I", len(c)) + c
+        else:
+            out += struct.pack("<I", len(raw) | 0x80000000) + raw
+    return bytes(out + struct.pack("<I", 0))
 
 
 def _fields(b):
@@ -58,6 +207,8 @@ def read_bag(path):
                 comp = h.get("compression", b"none")
                 if comp == b"bz2":
                     d = bz2.decompress(d)
+                elif comp == b"lz4":
+                    d = lz4_frame_decompress(d, struct.unpack("<I", h["size"])[0] if "size" in h else None)
                 elif comp != b"none":
                     raise ValueError(f"unsupported chunk compression {comp!r}")
                 walk(_records(d))
@@ -182,8 +333,9 @@ def _t(t):
     return struct.pack("<II", s, min(int(round((t - s) * 1e9)), 999999999))
 
 
-def write_bag(path, connections, messages, compression="none", chunk_bytes=1 << 20):
-    """connections: [(topic, type, md5sum, definition)], messages: [(conn_index, time, bytes)] in recording order."""
+def write_bag(path, connections, messages, compression="none", chunk_bytes=1 << 20, lz4_compress=None):
+    """connections: [(topic, type, md5sum, definition)], messages: [(conn_index, time, bytes)] in recording order.
+    lz4_compress: frame compressor to use instead of this module's (tests pass the system liblz4's)."""
     def conn_rec(i):
         topic, typ, md5, dfn = connections[i]
         d = _field("topic", topic.encode()) + _field("type", typ.encode()) + _field("md5sum", md5.encode()) + _field("message_definition", dfn.encode())
@@ -197,7 +349,7 @@ def write_bag(path, connections, messages, compression="none", chunk_bytes=1 << 
         if not chunk:
             return
         pos = len(MAGIC) + 4096 + len(body)
-        data = bz2.compress(chunk) if compression == "bz2" else chunk
+        data = bz2.compress(chunk) if compression == "bz2" else (lz4_compress or lz4_frame_compress)(chunk) if compression == "lz4" else chunk
         rec = _record([("op", bytes([OP_CHUNK])), ("compression", compression.encode()), ("size", struct.pack("<I", len(chunk)))], data)
         for cid, ents in index.items():
             rec += _record([("op", bytes([OP_INDEX])), ("ver", struct.pack("<I", 1)), ("conn", struct.pack("<I", cid)), ("count", struct.pack("<I", len(ents)))],

@@ -2,8 +2,8 @@
 """tools/run_bag.py BAG [--lidar /velodyne_points] [--imu /imu/data] [--max-scans N] [--lidar-model 0|1]
 
 BASELINE.json configs[1] runner (GPU box): replays a ROS1 bag through the restated front end (image projection, feature
-extraction, IMU propagation) and the B200 IESKF update, prints the trajectory.  Compressed bags: run
-`python tools/bag_tool.py decompress IN.bag OUT.bag` first (bz2)."""
+extraction, IMU propagation) and the B200 IESKF update, prints the trajectory.  Uncompressed and lz4-compressed bags
+are read directly; for bz2 run `python tools/bag_tool.py decompress IN.bag OUT.bag` first."""
 import argparse, importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
